@@ -1,0 +1,88 @@
+"""Build libabnn_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+    python -m abnn_b200.build [--force]
+
+-fmad=false keeps the plasticity arithmetic an unfused IEEE sequence (bit-parity with the oracle);
+-lineinfo lets ncu's source page map to these files.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libabnn_b200.so")
+OBJ = os.path.join(HERE, "_obj")
+SOURCES = ["traversal.cu", "exact.cu", "io_kernels.cu", "structural.cu", "init.cu", "capi.cu"]
+HOST_SOURCES = ["brain.cpp", "brain_engine.cpp", "manifest.cpp", "engine_capi.cpp"]
+NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false",
+              "-gencode", "arch=compute_100a,code=sm_100a",
+              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: libabnn_b200.so cannot be built (and there is no CPU fallback)")
+
+
+def _deps():
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    host = os.path.join(HERE, "host")
+    if os.path.isdir(host):
+        files += [os.path.join(host, f) for f in os.listdir(host)]
+    files.append(os.path.join(HERE, "..", "include", "abnn.h"))
+    files.append(os.path.abspath(__file__))
+    return files
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(f) > t for f in _deps() if os.path.isfile(f))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(OBJ, src + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src in HOST_SOURCES:
+        path = os.path.join(HERE, "host", src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(OBJ, src + ".o")
+        cmd = [nvcc, "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-Wall", "-I", os.path.join(HERE, "..", "include"),
+               "-c", path, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    link = [nvcc, "-shared", "-o", OUT] + objs + ["-lnccl", "-Xcompiler", "-fPIC"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

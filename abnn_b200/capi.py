@@ -77,7 +77,7 @@ class PassStats(C.Structure):
     _fields_ = [
         ("events", C.c_uint64), ("gated", C.c_uint64), ("fired", C.c_uint64),
         ("candidates", C.c_uint64), ("grown", C.c_uint64), ("clock", C.c_uint64),
-        ("device_ms", C.c_double),
+        ("device_ms", C.c_double), ("traverse_ms", C.c_double),
     ]
 
 
@@ -112,6 +112,8 @@ SIGNATURES = {
     "abnn_get_reward": (C.c_int, [_H, _P(C.c_float), _P(C.c_float)]),
     "abnn_run_pass": (C.c_int, [_H, C.c_uint64, _P(PassStats)]),
     "abnn_sync": (C.c_int, [_H]),
+    "abnn_timer_mark": (C.c_int, [_H, C.c_uint32]),
+    "abnn_timer_elapsed": (C.c_int, [_H, C.c_uint32, C.c_uint32, _P(C.c_double)]),
     "abnn_read_outputs": (C.c_int, [_H, C.c_void_p, C.c_uint32]),
     "abnn_readout_filtered": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_uint32]),
     "abnn_readout_step": (C.c_int, [_H, C.c_void_p, C.c_uint32]),

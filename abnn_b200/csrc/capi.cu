@@ -1,0 +1,867 @@
+// abnn_b200/csrc/capi.cu — implementation of the C-ABI in include/abnn.h.
+// Owns the device state that the reference's `Brain` owns as Metal buffers (brain.cpp:52-69) and
+// sequences the kernels of one pass on the handle's stream (Brain::encode_traversal, brain.cpp:87-122).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include <nccl.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace abnn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ABNN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+#define NC(call)                                                                                       \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != ncclSuccess)                                                                         \
+            return fail(ABNN_ERR_COMM, std::string(#call) + ": " + ncclGetErrorString(r_));            \
+    } while (0)
+#define RET(call)                                                                                      \
+    do { int rc_ = (call); if (rc_ != 0) return rc_; } while (0)
+
+constexpr int    RING = 16;             // pinned host staging slots for small per-pass vectors
+constexpr u64    UPLOAD_CHUNK = 8ull << 20;   // records per upload chunk (128 MB)
+constexpr u32    GROW_CAP_DEFAULT = 1u << 20;
+
+u32 next_pow2(u32 v) { u32 p = 1; while (p < v) p <<= 1; return p; }
+
+__global__ void k_set_reward(DevScalars* sc, float r) { sc->reward = r; }
+__global__ void k_set_clock(DevScalars* sc, u64 c) { sc->clock = c; }
+__global__ void k_reset_grow(DevScalars* sc) { sc->grow_count = 0; sc->grow_overflow = 0; }
+__global__ void k_pad_grow(GrowCand* c, u32 from, u32 to)
+{
+    const u32 i = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < to) c[i] = GrowCand{~0ull, 0xFFFFFFFFu, 0xFFFFFFFFu};
+}
+
+}  // namespace
+
+struct abnn_handle {
+    abnn_params p{};
+    int device = 0, sm_count = 0;
+    size_t l2_bytes = 0, l2_persist = 0;
+    u64 N = 0, slice = 0, lo = 0, hi = 0, npad = 0;
+    u64 n_local = 0, cap = 0;
+    std::vector<u64> n_local_all;
+    bool counts_dirty = false;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
+    cudaEvent_t timer[8]{};
+    abnn_synapse* d_syn = nullptr;
+    u64* d_ts = nullptr;
+    DevPtrs d{};
+    u32 grow_cap = 0, grow_buf = 0;
+    GrowCand* d_grow_all = nullptr; u32 grow_all_buf = 0;
+    float* d_vec = nullptr;               // RING slots of max(n_input,n_output) floats
+    float* h_vec = nullptr;               // pinned mirror
+    cudaEvent_t ring_ev[RING]{};
+    int ring_pos = 0;
+    u32 vec_len = 0;
+    ReadoutState rs{};
+    abnn_pass_stats* d_stats = nullptr;
+    void* h_pin = nullptr;                // pinned scratch (stats, scalars, spikes, rates)
+    size_t h_pin_bytes = 0;
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    abnn_synapse* d_stage = nullptr; u64 stage_cap = 0;
+    u64* d_total = nullptr;               // [0]: compaction total, [1..]: misc
+    u64* d_counts = nullptr;              // world_size u64 (record counts exchange)
+    ncclComm_t comm = nullptr;
+    bool timing = false;
+};
+
+namespace {
+
+int use(abnn_handle* h)
+{
+    if (!h) return fail(ABNN_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    return 0;
+}
+
+int ensure_scratch(abnn_handle* h, size_t bytes)
+{
+    if (bytes <= h->scratch_bytes) return 0;
+    if (h->d_scratch) CU(cudaFree(h->d_scratch));
+    h->d_scratch = nullptr; h->scratch_bytes = 0;
+    CU(cudaMalloc(&h->d_scratch, bytes));
+    h->scratch_bytes = bytes;
+    return 0;
+}
+
+// record counts of every rank (event shares, pass length) — exchanged lazily after the table changed
+int refresh_counts(abnn_handle* h)
+{
+    if (h->p.world_size == 1) { h->n_local_all.assign(1, h->n_local); h->counts_dirty = false; return 0; }
+    if (!h->counts_dirty) return 0;
+    if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
+    CU(cudaMemcpyAsync(h->d_counts + h->p.rank, &h->n_local, sizeof(u64), cudaMemcpyHostToDevice, h->st));
+    NC(ncclAllGather(h->d_counts + h->p.rank, h->d_counts, 1, ncclUint64, h->comm, h->st));
+    CU(cudaMemcpyAsync(h->n_local_all.data(), h->d_counts, sizeof(u64) * h->p.world_size, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->counts_dirty = false;
+    return 0;
+}
+
+void event_share(u64 events, u64 n_global, u64 before, u64 n_local, u64* first, u64* count)
+{
+    if (!n_global) { *first = 0; *count = 0; return; }
+    const u64 a = (u64)((unsigned __int128)events * before / n_global);
+    const u64 b = (u64)((unsigned __int128)events * (before + n_local) / n_global);
+    *first = a; *count = b - a;
+}
+
+KParams make_kparams(const abnn_handle* h, u64 events)
+{
+    const abnn_params& p = h->p;
+    KParams k{};
+    k.n_local = h->n_local;
+    u64 n_global = 0, acc = 0, maxc = 0, mine = 0;
+    for (u64 v : h->n_local_all) n_global += v;
+    for (u32 j = 0; j < p.world_size; ++j) {
+        u64 f, c;
+        event_share(events, n_global, acc, h->n_local_all[j], &f, &c);
+        if (j == p.rank) mine = c;
+        maxc = std::max(maxc, c);
+        acc += h->n_local_all[j];
+    }
+    k.count = mine; k.max_count = maxc;
+    k.ticks = std::max<u64>(1, (u64)p.world_size * maxc);
+    k.window_pre = p.window_pre; k.refractory = p.refractory;
+    k.n_neuron = h->N; k.neuron_lo = h->lo; k.neuron_hi = h->hi;
+    k.world = p.world_size; k.rank = p.rank; k.n_input = p.n_input;
+    k.sampler = p.sampler; k.release_rng = p.release_rng; k.clock_mode = p.clock_mode;
+    k.rbar_mode = p.rbar_mode; k.track_visits = p.track_visits; k.snapshot = p.src_view == ABNN_SRC_SNAPSHOT;
+    k.budget_on = p.max_spikes_per_pass != 0;
+    k.budget_share = (u32)((u64)p.max_spikes_per_pass * (p.rank + 1) / p.world_size -
+                           (u64)p.max_spikes_per_pass * p.rank / p.world_size);
+    k.grow_cap = h->grow_cap;
+    k.seed_lo = (u32)p.seed; k.seed_hi = (u32)(p.seed >> 32);
+    k.base_scale = p.base_scale; k.a_ltp = p.a_ltp; k.a_ltd = p.a_ltd; k.w_min = p.w_min; k.w_max = p.w_max;
+    k.eta_home = p.eta_home; k.target_rate_hz = p.target_rate_hz; k.home_tick_hz = p.home_tick_hz;
+    k.eta_reward = p.eta_reward; k.alpha_rbar = p.alpha_rbar; k.p_new = p.p_new;
+    return k;
+}
+
+// stage a small host vector into the next ring slot; returns the device pointer of the slot
+int stage_vec(abnn_handle* h, const float* v, u32 n, float** d_out)
+{
+    const int s = h->ring_pos;
+    h->ring_pos = (h->ring_pos + 1) % RING;
+    CU(cudaEventSynchronize(h->ring_ev[s]));           // slot's previous copy has drained
+    float* hp = h->h_vec + (size_t)s * h->vec_len;
+    float* dp = h->d_vec + (size_t)s * h->vec_len;
+    std::memcpy(hp, v, n * sizeof(float));
+    CU(cudaMemcpyAsync(dp, hp, n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    CU(cudaEventRecord(h->ring_ev[s], h->st));
+    *d_out = dp;
+    return 0;
+}
+
+int read_scalars(abnn_handle* h, DevScalars* out)
+{
+    CU(cudaMemcpyAsync(h->h_pin, h->d.sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    std::memcpy(out, h->h_pin, sizeof(DevScalars));
+    return 0;
+}
+
+// After the events of a pass: every rank's owned lastFired slice becomes visible to everyone
+// (per-pass allgather of fired-neuron timestamps over NVLink).
+int exchange_timestamps(abnn_handle* h)
+{
+    if (h->p.world_size > 1) {
+        if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
+        NC(ncclAllGather(h->d.live + h->lo, h->d.view, h->slice, ncclUint64, h->comm, h->st));
+    } else if (h->d.view != h->d.live) {
+        CU(cudaMemcpyAsync(h->d.view, h->d.live, h->N * sizeof(u64), cudaMemcpyDeviceToDevice, h->st));
+    }
+    return 0;
+}
+
+// Append a chunk of the global table: keep, in order, the records this rank owns.
+int append_chunk(abnn_handle* h, const abnn_synapse* host, u64 n)
+{
+    if (!n) return 0;
+    if (h->p.world_size == 1) {
+        if (h->n_local + n > h->cap) return fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded");
+        CU(cudaMemcpyAsync(h->d_syn + h->n_local, host, n * sizeof(abnn_synapse), cudaMemcpyHostToDevice, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        h->n_local += n;
+        return 0;
+    }
+    if (!h->d_stage) {
+        h->stage_cap = UPLOAD_CHUNK;
+        CU(cudaMalloc(&h->d_stage, h->stage_cap * sizeof(abnn_synapse)));
+    }
+    for (u64 off = 0; off < n; off += h->stage_cap) {
+        const u64 m = std::min(h->stage_cap, n - off);
+        CU(cudaMemcpyAsync(h->d_stage, host + off, m * sizeof(abnn_synapse), cudaMemcpyHostToDevice, h->st));
+        CompactArgs a{};
+        a.in = h->d_stage; a.out = h->d_syn + h->n_local; a.n = m; a.pred = KEEP_OWNED;
+        a.dst_lo = (u32)h->lo; a.dst_hi = (u32)h->hi; a.out_cap = h->cap - h->n_local;
+        RET(ensure_scratch(h, compact_scratch_bytes(m)));
+        CU(launch_compact(a, h->d_scratch, h->d_total, h->st));
+        u64 kept = 0;
+        CU(cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        if (kept > h->cap - h->n_local) return fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded (owned share larger than syn_capacity)");
+        h->n_local += kept;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* abnn_last_error(void) { return g_err.c_str(); }
+uint32_t abnn_abi_version(void) { return ABNN_ABI_VERSION; }
+
+int abnn_default_params(abnn_params* p, uint32_t profile)
+{
+    if (!p) return fail(ABNN_ERR_INVALID, "null params");
+    if (profile > ABNN_PROFILE_NORTH_STAR) return fail(ABNN_ERR_INVALID, "unknown profile");
+    std::memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(abnn_params); p->abi_version = ABNN_ABI_VERSION;
+    p->n_input = 256; p->n_output = 256; p->n_hidden = 5000000ull; p->n_syn = 1000000000ull;   // constants.h:2-5
+    p->seed = 42;                                                                               // simple.yml:12
+    if (profile == ABNN_PROFILE_METAL_PARITY) {
+        p->sampler = ABNN_SAMPLER_SWEEP; p->release_rng = ABNN_RNG_XORSHIFT;
+        p->clock_mode = ABNN_CLOCK_PER_PASS; p->exec_mode = ABNN_EXEC_SERIAL;
+        p->src_view = ABNN_SRC_LIVE; p->rbar_mode = ABNN_RBAR_METAL_TID0;
+        p->max_spikes_per_pass = 2560; p->track_visits = 0;                                     // brain.h:18
+        p->window_pre = 5; p->refractory = 2;                                                   // brain.metal:23-24
+    } else {
+        p->sampler = ABNN_SAMPLER_PHILOX; p->release_rng = ABNN_RNG_PHILOX;
+        p->clock_mode = ABNN_CLOCK_PER_EVENT; p->exec_mode = ABNN_EXEC_PARALLEL;
+        p->src_view = ABNN_SRC_SNAPSHOT; p->rbar_mode = ABNN_RBAR_PASS_STEP;
+        p->max_spikes_per_pass = 0; p->track_visits = 1;
+        p->window_pre = 50000; p->refractory = 2;                                               // brain.cpp:102
+    }
+    p->teacher_gap = 1;                                                                         // brain-engine.cpp:130
+    p->base_scale = 0.8f; p->a_ltp = 0.04f; p->a_ltd = 0.02f; p->w_min = 0.001f; p->w_max = 1.0f;
+    p->eta_home = 1.0e-6f; p->target_rate_hz = 1000.0f; p->home_tick_hz = 1e6f;
+    p->eta_reward = 1.0e-3f; p->alpha_rbar = 0.001f;
+    p->w_prune = 0.f; p->p_new = 0.f; p->w_init = 0.1f;
+    p->rate_alpha = 0.5f; p->peak_decay = 0.999f; p->peak_init = 0.5f;
+    p->use_fir = 1; p->fir_size = 20; p->reward_window = 1000;
+    p->filter_tau = 0.02; p->dt_sec = 0.0009; p->loss0 = 0.25;
+    p->device = -1; p->rank = 0; p->world_size = 1; p->l2_persist = 1;
+    return 0;
+}
+
+int abnn_partition(uint64_t n_neuron, uint32_t world, uint32_t rank, uint64_t* lo, uint64_t* hi)
+{
+    if (!world || rank >= world || !lo || !hi) return fail(ABNN_ERR_INVALID, "bad partition arguments");
+    const u64 slice = (n_neuron + world - 1) / world;
+    *lo = std::min<u64>(n_neuron, slice * rank);
+    *hi = std::min<u64>(n_neuron, slice * (rank + 1));
+    return 0;
+}
+int abnn_event_share(uint64_t events, uint64_t n_global, uint64_t before, uint64_t n_local, uint64_t* first, uint64_t* count)
+{
+    if (!first || !count) return fail(ABNN_ERR_INVALID, "null output");
+    u64 f, c; event_share(events, n_global, before, n_local, &f, &c);
+    *first = f; *count = c;
+    return 0;
+}
+void abnn_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    const Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// ---- lifetime -------------------------------------------------------------------------------------
+int abnn_create(const abnn_params* pp, abnn_handle** out)
+{
+    if (!pp || !out) return fail(ABNN_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const abnn_params& p = *pp;
+    if (p.struct_size != sizeof(abnn_params) || p.abi_version != ABNN_ABI_VERSION)
+        return fail(ABNN_ERR_INVALID, "abnn_params size/version mismatch (header and library differ)");
+    if (!p.world_size || p.rank >= p.world_size) return fail(ABNN_ERR_INVALID, "bad rank/world_size");
+    if (p.sampler > 1 || p.release_rng > 1 || p.clock_mode > 1 || p.exec_mode > 2 || p.src_view > 1 || p.rbar_mode > 1)
+        return fail(ABNN_ERR_INVALID, "unknown mode value");
+    if (!p.n_output || p.fir_size == 0 || p.fir_size > ABNN_MAX_FIR) return fail(ABNN_ERR_INVALID, "bad n_output / fir_size");
+    const u64 N = (u64)p.n_input + p.n_output + p.n_hidden;
+    if (N >= (1ull << 32)) return fail(ABNN_ERR_INVALID, "neuron ids are 32-bit (SynapsePacked.src/dst)");
+    if (p.src_view == ABNN_SRC_LIVE && p.world_size > 1)
+        return fail(ABNN_ERR_UNSUPPORTED, "LIVE src view is single-GPU only; sharded runs read the pass-start snapshot");
+    if (p.rbar_mode == ABNN_RBAR_METAL_TID0 && p.exec_mode != ABNN_EXEC_SERIAL)
+        return fail(ABNN_ERR_UNSUPPORTED, "METAL_TID0 r-bar needs SERIAL execution");
+    if (p.exec_mode == ABNN_EXEC_EXACT && p.src_view != ABNN_SRC_SNAPSHOT)
+        return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution needs the SNAPSHOT src view");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ABNN_ERR_NO_DEVICE, "no CUDA device: abnn_b200 has no CPU fallback");
+    }
+    int dev = p.device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(ABNN_ERR_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(dev));
+
+    abnn_handle* h = new abnn_handle;
+    h->p = p; h->device = dev; h->N = N;
+    h->slice = (N + p.world_size - 1) / p.world_size;
+    h->lo = std::min<u64>(N, h->slice * p.rank);
+    h->hi = std::min<u64>(N, h->slice * (p.rank + 1));
+    h->npad = h->slice * p.world_size;
+    h->n_local_all.assign(p.world_size, 0);
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); h->sm_count = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev); h->l2_bytes = (size_t)v;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+
+    h->cap = p.syn_capacity;
+    if (!h->cap) {
+        h->cap = p.world_size == 1 ? p.n_syn
+                                   : (p.n_syn + p.world_size - 1) / p.world_size + p.n_syn / (16ull * p.world_size) +
+                                         65536 + (u64)p.n_input * p.n_output;
+    }
+    if (!h->cap) h->cap = 1;
+
+#define CUH(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            abnn_destroy(h);                                                                           \
+            return fail(ABNN_ERR_CUDA, m_);                                                            \
+        }                                                                                              \
+    } while (0)
+
+    CUH(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CUH(cudaEventCreate(&h->ev0));
+    CUH(cudaEventCreate(&h->ev1));
+    CUH(cudaEventCreate(&h->evk));
+    for (int i = 0; i < 8; ++i) CUH(cudaEventCreate(&h->timer[i]));
+    for (int i = 0; i < RING; ++i) CUH(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    CUH(cudaMalloc(&h->d_syn, h->cap * sizeof(abnn_synapse)));
+    // timestamps: [view | visited | live] in one allocation so one access-policy window covers the
+    // two arrays every event touches (view read, visited RED); LIVE src view: [live | visited].
+    const u64 npad = (h->npad + 31) & ~31ull;
+    const bool snap = p.src_view == ABNN_SRC_SNAPSHOT;
+    const u64 arrays = snap ? 3 : 2;
+    CUH(cudaMalloc(&h->d_ts, arrays * npad * sizeof(u64)));
+    CUH(cudaMemsetAsync(h->d_ts, 0, arrays * npad * sizeof(u64), h->st));                      // brain.cpp:62-64
+    h->d.view = h->d_ts;
+    h->d.visited = h->d_ts + npad;
+    h->d.live = snap ? h->d_ts + 2 * npad : h->d_ts;
+    h->d.syn = h->d_syn;
+    CUH(cudaMalloc(&h->d.sc, sizeof(DevScalars)));
+    {
+        DevScalars s{};
+        s.max_observed = p.peak_init; s.last_loss = p.loss0; s.last_pass_ticks = 1;              // brain-engine.h:54,83
+        CUH(cudaMemcpy(h->d.sc, &s, sizeof(s), cudaMemcpyHostToDevice));
+    }
+    h->grow_cap = GROW_CAP_DEFAULT;
+    h->grow_buf = next_pow2(h->grow_cap);
+    if (p.p_new > 0.f) CUH(cudaMalloc(&h->d.grow, (size_t)h->grow_buf * sizeof(GrowCand)));
+    h->vec_len = std::max(p.n_input, p.n_output);
+    CUH(cudaMalloc(&h->d_vec, (size_t)RING * h->vec_len * sizeof(float)));
+    CUH(cudaMallocHost(&h->h_vec, (size_t)RING * h->vec_len * sizeof(float)));
+    CUH(cudaMalloc(&h->rs.rate, p.n_output * sizeof(float)));
+    CUH(cudaMalloc(&h->rs.iir, p.n_output * sizeof(float)));
+    CUH(cudaMalloc(&h->rs.fir, (size_t)p.fir_size * p.n_output * sizeof(float)));
+    CUH(cudaMalloc(&h->rs.smooth, p.n_output * sizeof(float)));
+    CUH(cudaMalloc(&h->rs.spikes, p.n_output));
+    CUH(cudaMemsetAsync(h->rs.rate, 0, p.n_output * sizeof(float), h->st));
+    CUH(cudaMemsetAsync(h->rs.iir, 0, p.n_output * sizeof(float), h->st));
+    CUH(cudaMemsetAsync(h->rs.fir, 0, (size_t)p.fir_size * p.n_output * sizeof(float), h->st));
+    CUH(cudaMemsetAsync(h->rs.smooth, 0, p.n_output * sizeof(float), h->st));
+    CUH(cudaMalloc(&h->d_stats, sizeof(abnn_pass_stats)));
+    CUH(cudaMemsetAsync(h->d_stats, 0, sizeof(abnn_pass_stats), h->st));
+    h->h_pin_bytes = std::max<size_t>(4096, (size_t)p.n_output * sizeof(float) * 2 + sizeof(DevScalars));
+    CUH(cudaMallocHost(&h->h_pin, h->h_pin_bytes));
+    CUH(cudaMalloc(&h->d_total, 8 * sizeof(u64)));
+    CUH(cudaMalloc(&h->d_counts, p.world_size * sizeof(u64)));
+
+    // L2 residency of the timestamp arrays (north star item 2)
+    if (p.l2_persist && max_persist > 0 && max_window > 0) {
+        const size_t hot = (size_t)2 * npad * sizeof(u64);
+        size_t want = std::min<size_t>(hot, (size_t)max_persist);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            size_t got = 0;
+            cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = h->d_ts;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(hot, (size_t)max_window);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)got / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(h->st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) h->l2_persist = got;
+        }
+        cudaGetLastError();
+    }
+    CUH(cudaStreamSynchronize(h->st));
+#undef CUH
+    *out = h;
+    return 0;
+}
+
+void abnn_destroy(abnn_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    if (h->comm) ncclCommDestroy(h->comm);
+    cudaFree(h->d_syn); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
+    cudaFree(h->d_vec); cudaFreeHost(h->h_vec);
+    cudaFree(h->rs.rate); cudaFree(h->rs.iir); cudaFree(h->rs.fir); cudaFree(h->rs.smooth); cudaFree(h->rs.spikes);
+    cudaFree(h->d_stats); cudaFreeHost(h->h_pin); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+    cudaFree(h->d_total); cudaFree(h->d_counts);
+    for (int i = 0; i < RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evk) cudaEventDestroy(h->evk);
+    for (int i = 0; i < 8; ++i) if (h->timer[i]) cudaEventDestroy(h->timer[i]);
+    if (h->st) cudaStreamDestroy(h->st);
+    cudaGetLastError();
+    delete h;
+}
+
+int abnn_get_info(abnn_handle* h, abnn_info* o)
+{
+    RET(use(h));
+    if (!o) return fail(ABNN_ERR_INVALID, "null output");
+    RET(refresh_counts(h));
+    DevScalars s; RET(read_scalars(h, &s));
+    std::memset(o, 0, sizeof(*o));
+    o->n_input = h->p.n_input; o->n_output = h->p.n_output; o->n_hidden = h->p.n_hidden; o->n_neuron = h->N;
+    for (u64 v : h->n_local_all) o->n_syn_global += v;
+    o->n_syn_local = h->n_local; o->syn_capacity = h->cap;
+    o->neuron_lo = h->lo; o->neuron_hi = h->hi; o->neuron_slice = h->slice;
+    o->rank = h->p.rank; o->world_size = h->p.world_size; o->device = h->device; o->sm_count = h->sm_count;
+    o->l2_bytes = h->l2_bytes; o->l2_persist_bytes = h->l2_persist;
+    o->pass_index = s.pass_index; o->clock = s.clock; o->event_base = s.event_base;
+    return 0;
+}
+
+// ---- communicator ---------------------------------------------------------------------------------
+int abnn_comm_unique_id(void* id128)
+{
+    if (!id128) return fail(ABNN_ERR_INVALID, "null id buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+int abnn_comm_init(abnn_handle* h, const void* id128)
+{
+    RET(use(h));
+    if (!id128) return fail(ABNN_ERR_INVALID, "null id");
+    if (h->comm) return fail(ABNN_ERR_INVALID, "communicator already initialised");
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NC(ncclCommInitRank(&h->comm, (int)h->p.world_size, id, (int)h->p.rank));
+    return 0;
+}
+
+// ---- graph ----------------------------------------------------------------------------------------
+int abnn_upload_synapses(abnn_handle* h, const abnn_synapse* syn, uint64_t n)
+{
+    RET(use(h));
+    if (!syn && n) return fail(ABNN_ERR_INVALID, "null table");
+    h->n_local = 0;
+    RET(append_chunk(h, syn, n));
+    h->counts_dirty = true;
+    if (h->p.world_size == 1) h->n_local_all.assign(1, h->n_local);
+    return 0;
+}
+
+int abnn_download_synapses(abnn_handle* h, abnn_synapse* out, uint64_t cap, uint64_t* n_out)
+{
+    RET(use(h));
+    if (n_out) *n_out = h->n_local;
+    if (cap < h->n_local) return fail(ABNN_ERR_CAPACITY, "output buffer smaller than the live table");
+    if (h->n_local && !out) return fail(ABNN_ERR_INVALID, "null output");
+    CU(cudaMemcpyAsync(out, h->d_syn, h->n_local * sizeof(abnn_synapse), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed)
+{
+    RET(use(h));
+    const abnn_params& p = h->p;
+    if (kind == ABNN_GRAPH_ER_BETA) {
+        const u64 g0 = (u64)((unsigned __int128)p.n_syn * p.rank / p.world_size);
+        const u64 g1 = (u64)((unsigned __int128)p.n_syn * (p.rank + 1) / p.world_size);
+        if (g1 - g0 > h->cap) return fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded");
+        if (h->hi == h->lo && g1 > g0) return fail(ABNN_ERR_INVALID, "rank owns no neurons");
+        CU(launch_init_er_beta(h->d_syn, g0, g1 - g0, seed, h->N, h->lo, h->hi, h->sm_count, h->st));
+        h->n_local = g1 - g0;
+        for (u32 k = 0; k < p.world_size; ++k)
+            h->n_local_all[k] = (u64)((unsigned __int128)p.n_syn * (k + 1) / p.world_size) -
+                                (u64)((unsigned __int128)p.n_syn * k / p.world_size);
+        h->counts_dirty = false;
+        return 0;
+    }
+    if (kind == ABNN_GRAPH_REFERENCE) {
+        // build_random_graph (brain-engine.cpp:31-53) streamed in chunks: mt19937(seed) [the reference
+        // seeds with 1], dense input->output w~U[.4,.8), then hidden->hidden w~U[.1,.2) with the
+        // draw order hid(src), hid(dst), wHH. Uses the host C++ library's distributions, as the
+        // reference does, so the table equals what the reference builds with this toolchain.
+        if (p.n_hidden == 0 && p.n_syn > (u64)p.n_input * p.n_output) return fail(ABNN_ERR_INVALID, "no hidden neurons for hidden->hidden edges");
+        std::mt19937 gen((uint32_t)seed);
+        std::uniform_real_distribution<float> wIn(0.4f, 0.8f), wHH(0.1f, 0.2f);
+        std::uniform_int_distribution<uint32_t> hid(p.n_input + p.n_output, (uint32_t)(h->N - 1));
+        const u64 chunk = std::min<u64>(UPLOAD_CHUNK, std::max<u64>(p.n_syn, 1));
+        std::vector<abnn_synapse> buf(chunk);
+        h->n_local = 0;
+        u64 idx = 0, fill = 0;
+        uint32_t i = 0, o = 0;
+        const u64 dense = std::min<u64>(p.n_syn, (u64)p.n_input * p.n_output);
+        while (idx < p.n_syn) {
+            if (idx < dense) {
+                buf[fill++] = abnn_synapse{i, p.n_input + o, wIn(gen), 0.f};
+                if (++o == p.n_output) { o = 0; ++i; }
+            } else {
+                const uint32_t a = hid(gen);
+                const uint32_t b = hid(gen);
+                const float    w = wHH(gen);
+                buf[fill++] = abnn_synapse{a, b, w, 0.f};
+            }
+            ++idx;
+            if (fill == chunk || idx == p.n_syn) { RET(append_chunk(h, buf.data(), fill)); fill = 0; }
+        }
+        h->counts_dirty = true;
+        if (p.world_size == 1) h->n_local_all.assign(1, h->n_local);
+        return 0;
+    }
+    return fail(ABNN_ERR_INVALID, "unknown graph kind");
+}
+
+// .bnn v1 (brain.cpp:161-178): u32 N_SYN, u32 N_NRN, N_SYN x 16 B, no padding.
+int abnn_save_bnn(abnn_handle* h, const char* path)
+{
+    RET(use(h));
+    if (!path) return fail(ABNN_ERR_INVALID, "null path");
+    if (h->p.world_size != 1) return fail(ABNN_ERR_UNSUPPORTED, ".bnn v1 holds one unsharded table; save from a single-GPU handle");
+    if (h->n_local >= (1ull << 32)) return fail(ABNN_ERR_UNSUPPORTED, ".bnn v1 header counts are 32-bit");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(ABNN_ERR_IO, std::string("cannot open for writing: ") + path);
+    const uint32_t hdr[2] = {(uint32_t)h->n_local, (uint32_t)h->N};
+    bool ok = std::fwrite(hdr, 4, 2, f) == 2;
+    const u64 chunk = 4ull << 20;
+    std::vector<abnn_synapse> buf(std::min<u64>(chunk, std::max<u64>(h->n_local, 1)));
+    for (u64 off = 0; ok && off < h->n_local; off += chunk) {
+        const u64 m = std::min(chunk, h->n_local - off);
+        if (cudaMemcpyAsync(buf.data(), h->d_syn + off, m * sizeof(abnn_synapse), cudaMemcpyDeviceToHost, h->st) != cudaSuccess ||
+            cudaStreamSynchronize(h->st) != cudaSuccess) { std::fclose(f); return fail(ABNN_ERR_CUDA, "device read failed during save"); }
+        ok = std::fwrite(buf.data(), sizeof(abnn_synapse), m, f) == m;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? 0 : fail(ABNN_ERR_IO, std::string("short write: ") + path);
+}
+
+int abnn_load_bnn(abnn_handle* h, const char* path)
+{
+    RET(use(h));
+    if (!path) return fail(ABNN_ERR_INVALID, "null path");
+    if (h->p.world_size != 1) return fail(ABNN_ERR_UNSUPPORTED, ".bnn v1 holds one unsharded table; load into a single-GPU handle");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(ABNN_ERR_IO, std::string("cannot open: ") + path);
+    uint32_t hdr[2] = {0, 0};
+    if (std::fread(hdr, 4, 2, f) != 2) { std::fclose(f); return fail(ABNN_ERR_IO, "short header"); }
+    if (!(hdr[0] == h->p.n_syn && hdr[1] == h->N)) {                                            // brain.cpp:174
+        std::fclose(f);
+        return fail(ABNN_ERR_SHAPE, ".bnn header (N_SYN, N_NRN) does not match the handle's shape");
+    }
+    const u64 n = hdr[0], chunk = 4ull << 20;
+    if (n > h->cap) { std::fclose(f); return fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded"); }
+    std::vector<abnn_synapse> buf(std::min<u64>(chunk, std::max<u64>(n, 1)));
+    for (u64 off = 0; off < n; off += chunk) {
+        const u64 m = std::min(chunk, n - off);
+        if (std::fread(buf.data(), sizeof(abnn_synapse), m, f) != m) { std::fclose(f); return fail(ABNN_ERR_IO, "short read"); }
+        if (cudaMemcpyAsync(h->d_syn + off, buf.data(), m * sizeof(abnn_synapse), cudaMemcpyHostToDevice, h->st) != cudaSuccess ||
+            cudaStreamSynchronize(h->st) != cudaSuccess) { std::fclose(f); return fail(ABNN_ERR_CUDA, "device write failed during load"); }
+    }
+    std::fclose(f);
+    h->n_local = n; h->n_local_all.assign(1, n); h->counts_dirty = false;
+    return 0;
+}
+
+// ---- per-pass operations --------------------------------------------------------------------------
+int abnn_inject_inputs(abnn_handle* h, const float* v, uint32_t n, float hz)
+{
+    RET(use(h));
+    if (!v || n != h->p.n_input) return fail(ABNN_ERR_INVALID, "inject_inputs: need n_input values (brain.cpp:75)");
+    const float pTick = hz * 1000u * 1000000000ull;      // hz * kTickNS * NSEC_PER_SEC (brain.cpp:76)
+    float* dv = nullptr;
+    RET(stage_vec(h, v, n, &dv));
+    const KParams kp = make_kparams(h, 0);
+    CU(launch_inject(kp, h->d, dv, n, pTick, h->st));
+    return 0;
+}
+
+int abnn_teacher_force(abnn_handle* h, const float* expected, uint32_t n, float rate)
+{
+    RET(use(h));
+    if (!expected || n != h->p.n_output) return fail(ABNN_ERR_INVALID, "teacher_force: need n_output values");
+    float* dv = nullptr;
+    RET(stage_vec(h, expected, n, &dv));
+    const KParams kp = make_kparams(h, 0);
+    CU(launch_teacher(kp, h->d, dv, n, rate, h->p.teacher_gap, h->st));
+    return 0;
+}
+
+int abnn_set_reward(abnn_handle* h, float reward)
+{
+    RET(use(h));
+    k_set_reward<<<1, 1, 0, h->st>>>(h->d.sc, reward);
+    CU(cudaGetLastError());
+    return 0;
+}
+int abnn_get_reward(abnn_handle* h, float* reward, float* rbar)
+{
+    RET(use(h));
+    DevScalars s; RET(read_scalars(h, &s));
+    if (reward) *reward = s.reward;
+    if (rbar) *rbar = s.rbar;
+    return 0;
+}
+
+int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
+{
+    RET(use(h));
+    RET(refresh_counts(h));
+    const KParams kp = make_kparams(h, events);
+    if (stats) CU(cudaEventRecord(h->ev0, h->st));
+    switch (h->p.exec_mode) {
+        case ABNN_EXEC_SERIAL:   CU(launch_traverse_serial(kp, h->d, h->st)); break;
+        case ABNN_EXEC_PARALLEL: CU(launch_traverse_parallel(kp, h->d, h->sm_count, h->st)); break;
+        default: return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution is not implemented in this build");
+    }
+    if (stats) CU(cudaEventRecord(h->evk, h->st));
+    CU(launch_end_pass(kp, h->d.sc, h->d_stats, h->st));
+    RET(exchange_timestamps(h));
+    if (stats) {
+        CU(cudaEventRecord(h->ev1, h->st));
+        CU(cudaMemcpyAsync(h->h_pin, h->d_stats, sizeof(abnn_pass_stats), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        std::memcpy(stats, h->h_pin, sizeof(abnn_pass_stats));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        stats->device_ms = ms;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->evk));
+        stats->traverse_ms = ms;
+    }
+    return 0;
+}
+
+int abnn_sync(abnn_handle* h)
+{
+    RET(use(h));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int abnn_timer_mark(abnn_handle* h, uint32_t slot)
+{
+    RET(use(h));
+    if (slot >= 8) return fail(ABNN_ERR_INVALID, "timer slot out of range");
+    CU(cudaEventRecord(h->timer[slot], h->st));
+    return 0;
+}
+int abnn_timer_elapsed(abnn_handle* h, uint32_t a, uint32_t b, double* ms)
+{
+    RET(use(h));
+    if (a >= 8 || b >= 8 || !ms) return fail(ABNN_ERR_INVALID, "bad timer arguments");
+    CU(cudaEventSynchronize(h->timer[b]));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, h->timer[a], h->timer[b]));
+    *ms = f;
+    return 0;
+}
+
+int abnn_read_outputs(abnn_handle* h, uint8_t* spikes, uint32_t n)
+{
+    RET(use(h));
+    if (!spikes || n != h->p.n_output) return fail(ABNN_ERR_INVALID, "read_outputs: need n_output slots");
+    const KParams kp = make_kparams(h, 0);
+    CU(launch_read_outputs(kp, h->d, h->rs.spikes, n, h->st));
+    CU(cudaMemcpyAsync(h->h_pin, h->rs.spikes, n, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    std::memcpy(spikes, h->h_pin, n);
+    return 0;
+}
+
+static int readout_enqueue(abnn_handle* h, const float* expected, uint32_t n)
+{
+    if (n != h->p.n_output) return fail(ABNN_ERR_INVALID, "readout: need n_output values");
+    float* de = nullptr;
+    if (expected) RET(stage_vec(h, expected, n, &de));
+    ReadoutParams rp{};
+    rp.n_input = h->p.n_input; rp.n_output = h->p.n_output;
+    rp.rate_alpha = h->p.rate_alpha; rp.peak_decay = h->p.peak_decay;
+    rp.use_fir = h->p.use_fir; rp.fir_size = h->p.fir_size; rp.reward_window = h->p.reward_window;
+    rp.a = h->p.dt_sec / (h->p.filter_tau + h->p.dt_sec);                                      // rate-filter.h:29
+    const KParams kp = make_kparams(h, 0);
+    CU(launch_readout(kp, h->d, rp, h->rs, de, h->st));
+    return 0;
+}
+int abnn_readout_step(abnn_handle* h, const float* expected, uint32_t n)
+{
+    RET(use(h));
+    return readout_enqueue(h, expected, n);
+}
+int abnn_readout_filtered(abnn_handle* h, const float* expected, float* rates, uint32_t n)
+{
+    RET(use(h));
+    RET(readout_enqueue(h, expected, n));
+    CU(cudaMemcpyAsync(h->h_pin, h->rs.smooth, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (rates) std::memcpy(rates, h->h_pin, n * sizeof(float));
+    return 0;
+}
+int abnn_get_loss(abnn_handle* h, double* last_loss, uint64_t* windows_done)
+{
+    RET(use(h));
+    DevScalars s; RET(read_scalars(h, &s));
+    if (last_loss) *last_loss = s.last_loss;
+    if (windows_done) *windows_done = s.windows_done;
+    return 0;
+}
+
+// ---- structural plasticity ------------------------------------------------------------------------
+int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
+{
+    RET(use(h));
+    abnn_structural_stats s{};
+    s.n_before = h->n_local;
+    // 1. prune: stable in-place compaction
+    if (h->p.w_prune > 0.f && h->n_local) {
+        CompactArgs a{};
+        a.in = h->d_syn; a.out = h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
+        a.out_cap = h->cap;
+        RET(ensure_scratch(h, compact_scratch_bytes(a.n)));
+        CU(launch_compact(a, h->d_scratch, h->d_total, h->st));
+        u64 kept = 0;
+        CU(cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        s.pruned = h->n_local - kept;
+        h->n_local = kept;
+    }
+    // 2. grow: candidates in event order
+    if (h->p.p_new > 0.f) {
+        DevScalars sc; RET(read_scalars(h, &sc));
+        if (sc.grow_overflow) {
+            k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
+            return fail(ABNN_ERR_CAPACITY, "growth staging buffer overflowed; call abnn_prune_and_grow more often");
+        }
+        u32 n = sc.grow_count;
+        GrowCand* list = h->d.grow;
+        u32 total = n;
+        if (h->p.world_size > 1) {
+            if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
+            // every rank needs everyone's candidates: exchange counts, pad to the maximum, allgather
+            u64 mine = n;
+            CU(cudaMemcpyAsync(h->d_counts + h->p.rank, &mine, sizeof(u64), cudaMemcpyHostToDevice, h->st));
+            NC(ncclAllGather(h->d_counts + h->p.rank, h->d_counts, 1, ncclUint64, h->comm, h->st));
+            std::vector<u64> cnt(h->p.world_size);
+            CU(cudaMemcpyAsync(cnt.data(), h->d_counts, sizeof(u64) * h->p.world_size, cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            u32 maxc = 0;
+            for (u64 c : cnt) maxc = std::max<u32>(maxc, (u32)c);
+            total = maxc * h->p.world_size;
+            const u32 need = next_pow2(std::max<u32>(total, 1));
+            if (need > h->grow_all_buf) {
+                if (h->d_grow_all) CU(cudaFree(h->d_grow_all));
+                h->d_grow_all = nullptr;
+                CU(cudaMalloc(&h->d_grow_all, (size_t)need * sizeof(GrowCand)));
+                h->grow_all_buf = need;
+            }
+            if (maxc) {
+                if (maxc > n) { k_pad_grow<<<(maxc - n + 255) / 256, 256, 0, h->st>>>(h->d.grow, n, maxc); CU(cudaGetLastError()); }
+                NC(ncclAllGather(h->d.grow, h->d_grow_all, (size_t)maxc * sizeof(GrowCand), ncclUint8, h->comm, h->st));
+            }
+            list = h->d_grow_all;
+        }
+        if (total) {
+            const u32 np2 = next_pow2(total);
+            CU(cudaMemsetAsync(h->d_total + 1, 0, sizeof(u64), h->st));
+            CU(launch_grow_sort_count(list, total, np2, (u32)h->lo, (u32)h->hi, reinterpret_cast<u32*>(h->d_total + 1), h->st));
+            u64 owned64 = 0;
+            CU(cudaMemcpyAsync(&owned64, h->d_total + 1, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            const u32 owned = (u32)owned64;
+            const u64 room = h->cap - h->n_local;
+            const u32 m = (u32)std::min<u64>(owned, room);
+            CU(launch_grow_append(list, m, h->d_syn, h->n_local, h->p.w_init, h->st));
+            h->n_local += m;
+            s.appended = m; s.dropped = owned - m;
+        }
+        k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->st));
+    s.n_after = h->n_local;
+    h->counts_dirty = true;
+    if (h->p.world_size == 1) h->n_local_all.assign(1, h->n_local);
+    if (out) *out = s;
+    return 0;
+}
+
+// ---- raw state access -----------------------------------------------------------------------------
+int abnn_download_timestamps(abnn_handle* h, uint64_t* lf, uint64_t* lv)
+{
+    RET(use(h));
+    // lastFired: the replicated view is what every rank agrees on after a pass; single GPU: live.
+    const u64* src = h->p.world_size > 1 ? h->d.view : h->d.live;
+    if (lf) CU(cudaMemcpyAsync(lf, src, h->N * sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+    if (lv) CU(cudaMemcpyAsync(lv, h->d.visited, h->N * sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int abnn_upload_timestamps(abnn_handle* h, const uint64_t* lf, const uint64_t* lv)
+{
+    RET(use(h));
+    if (lf) {
+        CU(cudaMemcpyAsync(h->d.live, lf, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
+        if (h->d.view != h->d.live) CU(cudaMemcpyAsync(h->d.view, lf, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
+    }
+    if (lv) CU(cudaMemcpyAsync(h->d.visited, lv, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int abnn_get_clock(abnn_handle* h, uint64_t* clock)
+{
+    RET(use(h));
+    if (!clock) return fail(ABNN_ERR_INVALID, "null output");
+    DevScalars s; RET(read_scalars(h, &s));
+    *clock = s.clock;
+    return 0;
+}
+int abnn_set_clock(abnn_handle* h, uint64_t clock)
+{
+    RET(use(h));
+    k_set_clock<<<1, 1, 0, h->st>>>(h->d.sc, clock);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// abnn_b200/csrc/common.cuh — shared definitions of the CUDA library behind include/abnn.h.
+// sm_100a only. Built with -fmad=false so the plasticity arithmetic of the rare path is the same
+// sequence of IEEE single-precision operations as the reference kernel (brain.metal:91-121).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/abnn.h"
+
+namespace abnn {
+
+typedef unsigned long long u64;
+typedef unsigned int       u32;
+
+// Philox counter layout: ctr = (idx.lo, idx.hi, aux, stream), key = seed.
+enum : u32 { STREAM_EVENT = 0, STREAM_GROW = 1, STREAM_INJECT = 2, STREAM_TEACHER = 3, STREAM_INIT = 4 };
+
+// Philox4x32-10 (Salmon et al., SC'11). One call serves one event: .x.y -> edge, .z -> release
+// draw, .w -> synaptogenesis trial. ~20 IMAD.WIDE + ~30 integer ops per event.
+struct Philox4 { u32 x, y, z, w; };
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u64 p0 = (u64)0xD2511F53u * c0;
+        const u64 p1 = (u64)0xCD9E8D57u * c2;
+        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0;
+        const u32 n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (u32)p1; c3 = (u32)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b)
+{
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+__host__ __device__ __forceinline__ float u01_24(u32 x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+__host__ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// rand01 of the reference kernel (brain.metal:15-19)
+__host__ __device__ __forceinline__ float rand01_xorshift(u32 s)
+{
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    return (float)(s & 0xFFFFFFu) * (1.0f / 16777216.0f);
+}
+
+// Growth candidate staged by a firing event; appended in `order` by the structural step.
+struct GrowCand { u64 order; u32 src, dst; };
+
+// Scalars that live on the device so that a pass needs no host round trip
+// (the reference keeps them in shared Metal buffers: brain.cpp:54-68).
+struct DevScalars {
+    u64   clock;             // bufClock_
+    u64   pass_index;
+    u64   event_base;        // Philox event index of local event 0 of the next pass
+    u64   tick_base;         // ordinal of tick 0 of the next pass (growth ordering)
+    u64   last_pass_ticks;   // span used by read_outputs
+    float reward;            // bufReward_
+    float rbar;              // bufRBar_
+    // per-pass counters (reset by the pass prologue)
+    u64   gated, fired, cands, grown_pass;
+    u32   fires_claimed;     // saturating budget (bufBudget_ counts down; this counts up)
+    u32   grow_count;        // staged growth candidates since the last structural step
+    u32   grow_overflow;
+    u32   pad0;
+    // read-out state (brain-engine.cpp:145-186; rate-filter.h)
+    float max_observed;
+    u32   iir_init;
+    u32   fir_count, fir_head;
+    u32   win_pos;
+    u32   pad1;
+    u64   windows_done;
+    double last_loss;
+    // compaction scratch
+    u64   compact_total;
+};
+
+// Everything a traversal kernel needs, passed by value (constant bank).
+struct KParams {
+    u64 n_local;         // live records in this rank's table
+    u64 count;           // events this rank executes this pass
+    u64 ticks;           // ticks this pass spans (G * max_k count_k, >= 1)
+    u64 max_count;
+    u64 window_pre, refractory;
+    u64 n_neuron, neuron_lo, neuron_hi;
+    u32 world, rank;
+    u32 n_input;
+    u32 sampler, release_rng, clock_mode, rbar_mode, track_visits, snapshot;
+    u32 budget_on;       // max_spikes_per_pass != 0
+    u32 budget_share;    // this rank's share of max_spikes_per_pass
+    u32 grow_cap;
+    u32 seed_lo, seed_hi;
+    float base_scale, a_ltp, a_ltd, w_min, w_max, eta_home, target_rate_hz, home_tick_hz, eta_reward, alpha_rbar;
+    float p_new;
+};
+
+struct DevPtrs {
+    abnn_synapse* syn;
+    u64* view;           // lastFired as seen for src reads (snapshot, or == live)
+    u64* live;           // lastFired, authoritative for the owned dst range (indexed by global id)
+    u64* visited;        // lastVisited
+    DevScalars* sc;
+    GrowCand* grow;
+};
+
+}  // namespace abnn

@@ -1,0 +1,50 @@
+// abnn_b200/csrc/kernels.h — host-callable launchers of the CUDA kernels (internal to the library).
+#pragma once
+#include "common.cuh"
+
+namespace abnn {
+
+// traversal.cu
+cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st);
+cudaError_t launch_traverse_serial(const KParams& kp, const DevPtrs& d, cudaStream_t st);
+cudaError_t launch_end_pass(const KParams& kp, DevScalars* sc, abnn_pass_stats* out, cudaStream_t st);
+
+// io_kernels.cu
+struct ReadoutParams {
+    u32 n_input, n_output;
+    float rate_alpha, peak_decay;
+    u32 use_fir, fir_size, reward_window;
+    double a;                       // dt / (tau + dt)   (rate-filter.h:29)
+};
+struct ReadoutState { float* rate; float* iir; float* fir; float* smooth; unsigned char* spikes; };
+cudaError_t launch_inject(const KParams& kp, const DevPtrs& d, const float* v, u32 n, float pTick, cudaStream_t st);
+cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* expected, u32 n, float rate, u64 gap, cudaStream_t st);
+cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st);
+cudaError_t launch_readout(const KParams& kp, const DevPtrs& d, const ReadoutParams& rp, const ReadoutState& rs,
+                           const float* expected, cudaStream_t st);
+
+// structural.cu
+enum CompactPredicate : u32 { KEEP_NOT_PRUNED = 0, KEEP_OWNED = 1 };
+struct CompactArgs {
+    const abnn_synapse* in;   // may alias out (in-place, out <= in)
+    abnn_synapse* out;
+    u64 n;
+    u64 out_cap;              // records `out` can hold; writes past it are dropped (total still counts them)
+    u32 pred;
+    float w_prune;
+    u32 dst_lo, dst_hi;
+};
+size_t compact_scratch_bytes(u64 n);
+// Stable stream compaction (single pass, decoupled look-back). Kept count lands in *d_total.
+cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cudaStream_t st);
+// Growth candidates c[0..n) (buffer holds n_pow2 >= n entries, n_pow2 a power of two): entries whose
+// dst is outside [dst_lo,dst_hi) and the padding get order = +inf, the owned ones are counted into
+// *d_owned (zeroed by the caller) and the buffer is sorted by `order` (bitonic).
+cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 n_pow2, u32 dst_lo, u32 dst_hi, u32* d_owned, cudaStream_t st);
+cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st);
+
+// init.cu
+cudaError_t launch_init_er_beta(abnn_synapse* syn, u64 g0, u64 count, u64 seed, u64 n_neuron, u64 dlo, u64 dhi,
+                                int sm_count, cudaStream_t st);
+
+}  // namespace abnn

@@ -1,0 +1,168 @@
+// abnn_b200/csrc/structural.cu — structural plasticity (README.md:120-127; absent from the reference
+// code) as deterministic, scan-based stream operations:
+//   * k_compact      : STABLE stream compaction of the synapse table in ONE pass over HBM
+//                      (16 B read per record + 16 B write per kept record), single-pass chained scan
+//                      with decoupled look-back. Works in place: a tile publishes its count only
+//                      after its records are in registers, and a tile's destination range never
+//                      reaches past its own source range, so no unread record is overwritten.
+//                      Used for pruning (keep !(w < w_prune)) and for the dst-owner filter of
+//                      abnn_upload_synapses.
+//   * k_grow_*       : growth candidates staged by firing events are ordered by the tick ordinal of
+//                      the event that produced them (bitonic sort) and appended in that order.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace abnn {
+
+namespace {
+constexpr int CT = 256;                 // threads per tile
+constexpr int CI = 8;                   // records per thread (128 B contiguous per thread)
+constexpr u64 TILE = (u64)CT * CI;
+#define FLAG_AGG    (1ull << 62)
+#define FLAG_PREFIX (2ull << 62)
+#define VAL_MASK    ((1ull << 62) - 1)
+
+__device__ __forceinline__ bool keep_record(const CompactArgs& a, const uint4& r)
+{
+    if (a.pred == KEEP_NOT_PRUNED) return !(__uint_as_float(r.z) < a.w_prune);
+    return r.y >= a.dst_lo && r.y < a.dst_hi;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(CT) k_compact(const CompactArgs a, u32* ticket, volatile u64* desc, u64* total)
+{
+    __shared__ u32 s_tile;
+    __shared__ u32 s_warp[CT / 32];
+    __shared__ u64 s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);     // tiles are taken in table order
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 base = (u64)tile * TILE + (u64)threadIdx.x * CI;
+    const uint4* in = reinterpret_cast<const uint4*>(a.in);
+    uint4 rec[CI];
+    u32 keep = 0, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+        if (base + j < a.n) {
+            rec[j] = in[base + j];
+            if (keep_record(a, rec[j])) { keep |= 1u << j; ++cnt; }
+        }
+    }
+    // block-wide exclusive scan of cnt
+    u32 inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    u32 warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < CT / 32; ++w) { const u32 v = s_warp[w]; if (w < (int)warp) warp_off += v; block_total += v; }
+    const u32 excl = warp_off + inc - cnt;
+
+    // chained scan across tiles: warp 0 looks back 32 predecessors at a time
+    if (warp == 0) {
+        u64 run = 0;
+        if (tile == 0) {
+            if (lane == 0) desc[0] = FLAG_PREFIX | block_total;
+        } else {
+            if (lane == 0) desc[tile] = FLAG_AGG | block_total;
+            long long p = (long long)tile - 1;
+            while (true) {
+                const long long idx = p - lane;
+                u64 v = FLAG_PREFIX;                                       // before the table: prefix 0
+                if (idx >= 0) v = desc[idx];
+                const unsigned inval = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+                const unsigned pref  = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                if (pref) {
+                    const int fp = __ffs(pref) - 1;
+                    const unsigned need = fp == 31 ? 0xffffffffu : ((2u << fp) - 1u);
+                    if (inval & need) continue;
+                    u64 part = lane <= (unsigned)fp ? (v & VAL_MASK) : 0;
+                    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    run += part;
+                    break;
+                }
+                if (inval) continue;
+                u64 part = v & VAL_MASK;
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                run += part;
+                p -= 32;
+            }
+            if (lane == 0) desc[tile] = FLAG_PREFIX | (run + block_total);
+        }
+        if (lane == 0) {
+            s_prefix = run;
+            if ((u64)(tile + 1) * TILE >= a.n) *total = run + block_total;  // last tile
+        }
+    }
+    __syncthreads();
+    uint4* out = reinterpret_cast<uint4*>(a.out);
+    u64 pos = s_prefix + excl;
+#pragma unroll
+    for (int j = 0; j < CI; ++j)
+        if (keep & (1u << j)) { if (pos < a.out_cap) out[pos] = rec[j]; ++pos; }
+}
+
+size_t compact_scratch_bytes(u64 n)
+{
+    const u64 tiles = (n + TILE - 1) / TILE;
+    return 16 + (size_t)(tiles + 1) * sizeof(u64);
+}
+
+cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cudaStream_t st)
+{
+    const u64 tiles = (a.n + TILE - 1) / TILE;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, compact_scratch_bytes(a.n), st);
+    if (e != cudaSuccess) return e;
+    if (tiles == 0) return cudaMemsetAsync(d_total, 0, sizeof(u64), st);
+    u32* ticket = reinterpret_cast<u32*>(scratch);
+    u64* desc = reinterpret_cast<u64*>(reinterpret_cast<char*>(scratch) + 16);
+    k_compact<<<(unsigned)tiles, CT, 0, st>>>(a, ticket, desc, d_total);
+    return cudaGetLastError();
+}
+
+// ---- growth -------------------------------------------------------------------------------------
+__global__ void k_grow_prepare(GrowCand* c, u32 n, u32 n_pow2, u32 dst_lo, u32 dst_hi, u32* owned)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pow2) return;
+    bool mine = false;
+    if (i < n) mine = c[i].dst >= dst_lo && c[i].dst < dst_hi;
+    if (!mine) c[i].order = ~0ull;                     // foreign / padding entries sink to the end
+    const unsigned m = __ballot_sync(__activemask(), mine);
+    if (mine && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(owned, (u32)__popc(m));
+}
+__global__ void k_bitonic_step(GrowCand* c, u32 n_pow2, u32 j, u32 k)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pow2) return;
+    const u32 l = i ^ j;
+    if (l <= i) return;
+    const GrowCand a = c[i], b = c[l];
+    const bool asc = (i & k) == 0;
+    if ((a.order > b.order) == asc) { c[i] = b; c[l] = a; }
+}
+__global__ void k_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) syn[at + i] = abnn_synapse{c[i].src, c[i].dst, w_init, 0.f};
+}
+
+cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 n_pow2, u32 dst_lo, u32 dst_hi, u32* d_owned, cudaStream_t st)
+{
+    if (!n_pow2) return cudaSuccess;
+    const unsigned blocks = (n_pow2 + 255) / 256;
+    k_grow_prepare<<<blocks, 256, 0, st>>>(c, n, n_pow2, dst_lo, dst_hi, d_owned);
+    for (u32 k = 2; k <= n_pow2; k <<= 1)
+        for (u32 j = k >> 1; j > 0; j >>= 1) k_bitonic_step<<<blocks, 256, 0, st>>>(c, n_pow2, j, k);
+    return cudaGetLastError();
+}
+cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st)
+{
+    if (!m) return cudaSuccess;
+    k_grow_append<<<(m + 255) / 256, 256, 0, st>>>(c, m, syn, at, w_init);
+    return cudaGetLastError();
+}
+
+}  // namespace abnn

@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — synaptic events/s of the ABNN traversal hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one engine pass over one synthetic stimulus frame: inject sine input -> teacher forcing
+-> EVENTS_PER_PASS traversal events -> (N>1) NCCL allgather of lastFired slices -> FIR read-out and
+reward step. Workload = BASELINE.json configs[2] (the shape the metric is quoted on): 5,000,000
+hidden + 256 in + 256 out neurons, 1,000,000,000 synapses (16 GB SynapsePacked), 150,000,000 events
+per pass; for N>1 the same table is dst-sharded over the ranks (configs[3], strong scaling).
+
+  value    : whole-job events/s, device-timed (CUDA events on the handle's stream), state resident in HBM.
+  e2e      : the same through the reference-facing per-pass API with HOST buffers: stimulus vectors are
+             copied host->device and the filtered read-out device->host every pass, wall clock between syncs.
+  roofline : traversal kernel alone: events * B_alg / kernel time vs MEASURED_PEAKS.json hbm_gbs,
+             B_alg = 16 B + 16 B * gated fraction; traffic = ncu DRAM bytes (profiles/).
+  cpu_baseline : the oracle (host C++ restatement, oracle/oracle_b.cpp) on all host threads, bounded sample.
+--impl reference : the reference ships no CPU traversal and its Metal/AppKit app cannot be built here
+  (DESIGN.md §6); this arm times the oracle port of the reference algorithm on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_IN, N_OUT = 256, 256
+HBM_FALLBACK_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hidden", type=int, default=5_000_000)
+    ap.add_argument("--syn", type=int, default=1_000_000_000)
+    ap.add_argument("--events", type=int, default=150_000_000)
+    ap.add_argument("--sampler", default="philox", choices=["philox", "sweep"])
+    ap.add_argument("--warm-frac", type=float, default=0.25,
+                    help="fraction of neurons whose lastFired is pre-seeded inside the pre-spike window (SURVEY §8d 'warm' variant)")
+    ap.add_argument("--no-visits", action="store_true")
+    ap.add_argument("--no-l2-persist", action="store_true")
+    ap.add_argument("--cpu-syn", type=int, default=100_000_000)
+    ap.add_argument("--cpu-events", type=int, default=20_000_000)
+    ap.add_argument("--skip-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def stimulus_frames(n):
+    from abnn_b200 import FunctionalDataset
+    d = FunctionalDataset(N_IN, N_OUT)
+    fin, fex = [], []
+    for _ in range(n):
+        fin.append(d.nextInput()); fex.append(d.nextExpected())
+    return np.stack(fin), np.stack(fex)
+
+
+def base_params(args, O, capi, rank, world, events):
+    # North-star profile; the pre-spike window / refractory period are the reference's 5 / 2 PASSES
+    # (brain.metal:23-24) expressed in per-event ticks (one pass = `events` ticks).
+    over = dict(n_input=N_IN, n_output=N_OUT, n_hidden=args.hidden, n_syn=args.syn, seed=42,
+                sampler=capi.SAMPLER_PHILOX if args.sampler == "philox" else capi.SAMPLER_SWEEP,
+                exec_mode=capi.EXEC_PARALLEL, window_pre=5 * events, refractory=2 * events,
+                track_visits=0 if args.no_visits else 1, l2_persist=0 if args.no_l2_persist else 1,
+                rank=rank, world_size=world, device=-1)
+    return O.default_params(capi.PROFILE_NORTH_STAR, **over)
+
+
+def warm_timestamps(n_neuron, frac, events, seed=7):
+    """Pre-seed lastFired of `frac` of the neurons uniformly inside the pre-spike window so that the
+    gated fraction is non-trivial from the first timed pass; clock starts after the window."""
+    rng = np.random.default_rng(seed)
+    lf = np.zeros(n_neuron, np.uint64)
+    k = int(n_neuron * frac)
+    idx = rng.choice(n_neuron, size=k, replace=False)
+    start = 6 * events
+    lf[idx] = rng.integers(start - 5 * events, start, size=k).astype(np.uint64)
+    return lf, start
+
+
+def run_cpu(args, steps, warmup, as_reference):
+    """Oracle port on all host threads: T dst-shards, one thread each (same partition as multi-GPU)."""
+    from abnn_b200 import capi
+    from oracle import pyoracle as O
+    T = os.cpu_count() or 1
+    syn, events = args.cpu_syn, args.cpu_events
+    p = base_params(args, O, capi, 0, 1, events)
+    p.n_syn = syn
+    p.exec_mode = capi.EXEC_SERIAL
+    world = O.OracleWorld(p, T)
+    th = [threading.Thread(target=s.init_graph, args=(capi.GRAPH_ER_BETA, 1)) for s in world.shards]
+    [t.start() for t in th]; [t.join() for t in th]
+    world._sync_counts()
+    n_neuron = N_IN + N_OUT + args.hidden
+    lf, start = warm_timestamps(n_neuron, args.warm_frac, events)
+    for s in world.shards:
+        s.upload_timestamps(lf, None); s.clock = start; s.set_reward(0.01)
+    fin, fex = stimulus_frames(steps + warmup)
+    times, gated = [], 0
+    for it in range(steps + warmup):
+        t0 = time.perf_counter()
+        for s in world.shards:
+            s.inject_inputs(fin[it], 1000.0); s.teacher_force(fex[it], float(it & 1))
+        st = world.run_pass(events)
+        world.shards[0].readout_filtered(fex[it])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt); gated += st.gated
+    ms = 1e3 * float(np.mean(times))
+    val = events / (ms * 1e-3)
+    sample = (f"{steps} passes x {events:,} events on a {syn:,}-synapse / {n_neuron:,}-neuron ER-Beta graph "
+              f"(same per-event work, table {syn * 16 / 1e9:.1f} GB instead of {args.syn * 16 / 1e9:.1f} GB), "
+              f"{T} dst-shards on {T} threads")
+    return val, ms, T, sample, gated / max(1, steps * events)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 0)
+    workload = (f"constants.h shape: {args.hidden:,} hidden + {N_IN} in + {N_OUT} out, {args.syn:,} synapses "
+                f"({args.syn * 16 / 1e9:.1f} GB SynapsePacked), {args.events:,} events/pass")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, ms, T, sample, g = run_cpu(args, max(1, min(K, 5)), min(W, 1), True)
+        print(json.dumps({
+            "impl": "reference", "metric": "synaptic events/sec", "value": val, "unit": "events/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64 timestamps + f32 weights", "data": "synthetic",
+            "config": {"workload": workload, "sampler": args.sampler, "l2": "inputs larger than L2"},
+            "cpu_baseline": {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample,
+                             "gated_fraction": g},
+            "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference has no CPU traversal and its Metal app cannot be built on Linux; this is the oracle port of its algorithm"}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from abnn_b200 import Brain, capi
+    from oracle import pyoracle as O      # parameter defaults + cpu_baseline leg only
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    p = base_params(args, O, capi, rank, world, args.events)
+    p.device = local_rank
+    b = Brain(p)
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes as C
+            raw = C.create_string_buffer(128)
+            capi.check(b.lib.abnn_comm_unique_id(raw), "abnn_comm_unique_id")
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        b.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+    b.init_graph(capi.GRAPH_ER_BETA, 1)
+    n_neuron = N_IN + N_OUT + args.hidden
+    lf, start = warm_timestamps(n_neuron, args.warm_frac, args.events)
+    b.upload_timestamps(lf, None)
+    b.clock = start
+    b.set_reward(0.01)
+    info = b.info()
+    fin, fex = stimulus_frames(2 * (K + W))
+    pin_in = torch.from_numpy(fin).pin_memory().numpy()
+    pin_ex = torch.from_numpy(fex).pin_memory().numpy()
+
+    def barrier():
+        b.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step_device(it):
+        b.inject_inputs(pin_in[it], 1000.0)
+        b.teacher_force(pin_ex[it], float(it & 1))
+        b.encode_traversal(args.events)
+        b.readout_step(pin_ex[it])
+
+    # ---- value: device-timed, K steps ------------------------------------------------------------
+    for it in range(W):
+        step_device(it)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    b.timer_mark(0)
+    for it in range(W, W + K):
+        step_device(it)
+    b.timer_mark(1)
+    barrier()
+    ms_total = b.timer_elapsed(0, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline: traversal kernel alone, per launch (CUDA events around the kernel) ---------------
+    trav_ms, gated, fired, evs = [], 0, 0, 0
+    for it in range(min(K, 10)):
+        b.inject_inputs(pin_in[W + K + it], 1000.0)
+        b.teacher_force(pin_ex[W + K + it], float(it & 1))
+        st = b.run_pass(args.events)
+        trav_ms.append(st.traverse_ms); gated += st.gated; fired += st.fired; evs += st.events
+    barrier()
+
+    # ---- e2e: host buffers in, filtered read-out back to the host, every step -----------------------
+    t0 = time.perf_counter()
+    for it in range(K):
+        j = (W + K + 10 + it) % len(pin_in)
+        b.inject_inputs(pin_in[j], 1000.0)
+        b.teacher_force(pin_ex[j], float(it & 1))
+        b.encode_traversal(args.events)
+        b.readout_filtered(pin_ex[j])          # D2H + sync
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s, float(np.mean(trav_ms))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([gated, fired, evs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms_total, e2e_s, trav_mean = (float(x) for x in t.tolist())
+        gated, fired, evs = (float(x) for x in cnt.tolist())
+    else:
+        trav_mean = float(np.mean(trav_ms))
+
+    if rank == 0:
+        ms_step = ms_total / K
+        value = args.events / (ms_step * 1e-3)
+        g = gated / max(1.0, evs)
+        b_alg = 16.0 + 16.0 * g
+        peak, peak_kind = peaks()
+        # per-GPU roofline of the traversal kernel: this rank's events per launch
+        ev_per_launch = evs / (min(K, 10) * world)
+        achieved = ev_per_launch * b_alg / (trav_mean * 1e-3) / 1e9
+        line = {
+            "metric": "synaptic events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 timestamps + f32 weights", "data": "synthetic",
+            "config": {"workload": workload, "sampler": args.sampler, "exec_mode": "parallel", "clock": "per_event",
+                       "graph": "ER endpoints, Beta(2,8) weights (Philox)", "window_pre_passes": 5, "refractory_passes": 2,
+                       "warm_fraction": args.warm_frac, "track_visits": not args.no_visits,
+                       "parallelism": f"dst-shard x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (16 GB table, random gathers)",
+                       "l2_persist_bytes": int(info.l2_persist_bytes)},
+            "gated_fraction": g, "fire_fraction": fired / max(1.0, evs),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_traverse_parallel",
+                         "kernel_ms": trav_mean, "alg_bytes_per_event": b_alg,
+                         "sector_level_frac": ev_per_launch * (32.0 + 32.0 * g) / (trav_mean * 1e-3) / 1e9 / peak},
+            "e2e": {"value": args.events * K / e2e_s, "unit": "events/s",
+                    "h2d_bytes_per_step": int(3 * N_IN * 4), "d2h_bytes_per_step": int(N_OUT * 4)},
+            "gpu_launches": 5 * K,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.skip_cpu:
+            val, ms, T, sample, gc = run_cpu(args, 3, 1, False)
+            line["cpu_baseline"] = {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample,
+                                    "gated_fraction": gc}
+        print(json.dumps(line))
+    b.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

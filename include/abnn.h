@@ -172,6 +172,7 @@ typedef struct abnn_pass_stats {
     uint64_t grown;         /* synaptogenesis candidates staged this pass                       */
     uint64_t clock;         /* clock after the pass                                             */
     double   device_ms;     /* device time of the pass (CUDA events), incl. timestamp exchange  */
+    double   traverse_ms;   /* device time of the traversal kernel(s) alone                     */
 } abnn_pass_stats;
 
 typedef struct abnn_structural_stats {
@@ -220,6 +221,11 @@ int abnn_get_reward(abnn_handle* h, float* reward, float* rbar);         /* sync
  * `events` events. Asynchronous when stats == NULL; otherwise synchronises and fills *stats. */
 int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats);
 int abnn_sync(abnn_handle* h);                                           /* waitUntilCompleted */
+/* Device-side stopwatch on the handle's stream (CUDA events; the stream is private to the handle, so
+ * callers cannot time it with their own events): mark slot 0..7, then read the time between two marks.
+ * abnn_timer_elapsed synchronises. */
+int abnn_timer_mark(abnn_handle* h, uint32_t slot);
+int abnn_timer_elapsed(abnn_handle* h, uint32_t slot_from, uint32_t slot_to, double* ms);
 /* Brain::read_outputs (brain.cpp:145-157): spikes[o] = output o fired during the last pass. Synchronises. */
 int abnn_read_outputs(abnn_handle* h, uint8_t* spikes, uint32_t n);
 /* Rate EMA + RateFilter::process + peak normalise (+ loss/reward every reward_window passes when

@@ -1,0 +1,225 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): SERIAL / conflict-free execution bit-exact on fire decisions,
+timestamps, prune/append order; weights here are also required bit-exact (tolerance 0, tighter
+than the 1e-6 relative the north star allows). Fully PARALLEL execution: statistical bounds,
+stated per test.
+"""
+import numpy as np
+import pytest
+
+from abnn_b200 import Brain, BrainEngine, FunctionalDataset, capi
+from oracle import pyoracle as O
+from tests.helpers import assert_same_state, assert_same_stats, random_graph
+from tests.test_oracle import kat_graph
+
+pytestmark = pytest.mark.gpu
+
+TOY = dict(n_input=256, n_output=256, n_hidden=10_000, n_syn=1_000_000)   # BASELINE.json configs[0]
+
+
+def pair(profile, **over):
+    p = O.default_params(profile, **over)
+    return Brain(p), O.OracleB(p)
+
+
+# ---- metal-parity profile: the reference kernel itself -------------------------------------------
+def test_metal_parity_kat_vs_verbatim_reference_kernel():
+    """GPU SERIAL metal-parity == brain.metal compiled verbatim (Oracle A), SURVEY.md §8c KAT."""
+    syn = kat_graph()
+    b, o = pair(capi.PROFILE_METAL_PARITY, n_input=16, n_output=16, n_hidden=32, n_syn=1024)
+    b.upload_synapses(syn); o.upload_synapses(syn)
+    b.set_reward(0.1); o.set_reward(0.1)
+    a = O.OracleA(syn, 64, reward=0.1, hold_clock=True) if O.have_ref() else None
+    for p in range(8):
+        sb, so = b.run_pass(1024), o.run_pass(1024)
+        assert_same_stats(sb, so, f"pass {p}")
+        assert_same_state(b, o, f"pass {p}")
+        if a is not None:
+            a.run_pass(1024)
+            assert b.download_synapses().tobytes() == a.syn.tobytes()
+            assert np.array_equal(b.timestamps()[0], a.lastF.astype(np.uint64))
+            assert 2560 - sb.fired == a.st.budget
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_metal_parity_random_graph(seed):
+    rng = np.random.default_rng(seed)
+    N, n = 512, 256 * 40
+    syn = random_graph(rng, n, N)
+    pre = rng.integers(1, 12, N).astype(np.uint64)
+    b, o = pair(capi.PROFILE_METAL_PARITY, n_input=16, n_output=16, n_hidden=N - 32, n_syn=n)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(pre, None); x.clock = int(pre.max()) + 1; x.set_reward(0.2 * seed - 0.3)
+    for p in range(10):
+        assert_same_stats(b.run_pass(n), o.run_pass(n), f"pass {p}")
+        assert_same_state(b, o, f"pass {p}")
+
+
+# ---- north-star profile, SERIAL execution: bit-exact ------------------------------------------------
+def test_north_star_serial_toy_engine_loop():
+    """configs[0] shape (256/256/10k, 1M synapses): reference graph, sine input, teacher forcing, reward,
+    read-out; events per pass reduced to 150k so the serial walk finishes in seconds."""
+    over = dict(TOY, exec_mode=capi.EXEC_SERIAL, window_pre=400_000, refractory=50_000, seed=42, p_new=0.05)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.build_random_graph(1); o.init_graph(capi.GRAPH_REFERENCE, 1)
+    stim = FunctionalDataset()
+    even = False
+    total_fired = 0
+    for p in range(6):
+        vin, exp = stim.nextInput(), stim.nextExpected()
+        for x in (b, o):
+            x.inject_inputs(vin, 1000.0)
+            x.teacher_force(exp, 1.0 if even else 0.0)
+        even = not even
+        sb, so = b.run_pass(150_000), o.run_pass(150_000)
+        assert_same_stats(sb, so, f"pass {p}")
+        total_fired += so.fired
+        assert np.array_equal(b.read_outputs(), o.read_outputs())
+        rb, ro = b.readout_filtered(exp), o.readout_filtered(exp)
+        assert rb.tobytes() == ro.tobytes(), f"filtered read-out differs at pass {p}"
+        if p == 2:
+            b.set_reward(0.05); o.set_reward(0.05)
+    assert_same_state(b, o, "after 6 passes")
+    assert total_fired > 100, "workload degenerate: nothing fired"
+    sb, so = b.prune_and_grow(), o.prune_and_grow()
+    assert (sb.appended, sb.pruned, sb.n_after) == (so.appended, so.pruned, so.n_after) and so.appended > 0
+    assert_same_state(b, o, "after growth")
+
+
+def test_north_star_serial_per_pass_clock_and_budget():
+    rng = np.random.default_rng(5)
+    N, n = 4096, 200_000
+    syn = random_graph(rng, n, N, 0.5, 1.0)
+    pre = rng.integers(1, 9, N).astype(np.uint64)
+    over = dict(n_input=32, n_output=32, n_hidden=N - 64, n_syn=n, exec_mode=capi.EXEC_SERIAL,
+                clock_mode=capi.CLOCK_PER_PASS, window_pre=5, refractory=2, max_spikes_per_pass=500)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(pre, None); x.clock = 9; x.set_reward(-0.1)
+    for p in range(4):
+        sb, so = b.run_pass(60_000), o.run_pass(60_000)
+        assert_same_stats(sb, so, f"pass {p}")
+        assert so.fired <= 500
+    assert_same_state(b, o)
+
+
+# ---- PARALLEL execution ------------------------------------------------------------------------------
+def test_parallel_conflict_free_is_bit_exact():
+    """When no two events of a pass share a destination, PARALLEL == SERIAL order bit for bit:
+    SWEEP over a table whose dst values are a permutation (each dst once), unlimited budget."""
+    rng = np.random.default_rng(11)
+    N = 1 << 16
+    syn = np.zeros(N, O.SYN_DTYPE)
+    syn["src"] = rng.integers(0, N, N)
+    syn["dst"] = rng.permutation(N)
+    syn["w"] = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    pre = rng.integers(1, 30_000, N).astype(np.uint64)
+    for clock_mode, win, refr in ((capi.CLOCK_PER_EVENT, 60_000, 20_000), (capi.CLOCK_PER_PASS, 5, 2)):
+        over = dict(n_input=64, n_output=64, n_hidden=N - 128, n_syn=N, sampler=capi.SAMPLER_SWEEP,
+                    exec_mode=capi.EXEC_PARALLEL, clock_mode=clock_mode, window_pre=win, refractory=refr)
+        b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+        pre_c = pre if clock_mode == capi.CLOCK_PER_EVENT else (pre % 7 + 1)
+        for x in (b, o):
+            x.upload_synapses(syn); x.upload_timestamps(pre_c, None); x.clock = int(pre_c.max()) + 1; x.set_reward(0.3)
+        for p in range(3):
+            sb, so = b.run_pass(N), o.run_pass(N)
+            assert_same_stats(sb, so, f"mode {clock_mode} pass {p}")
+            assert so.gated > 1000
+        assert_same_state(b, o, f"clock mode {clock_mode}")
+
+
+def test_parallel_statistical_parity_toy():
+    """configs[0] at full size (1M synapses, 1M-event passes), fully parallel. Bounds: gated and fired
+    counts within 2 % of the oracle's (+ 5 sigma Poisson), mean weight within 1e-4 absolute, weight
+    histogram L1 distance below 1 %, lastVisited identical (order-free max)."""
+    over = dict(TOY, exec_mode=capi.EXEC_PARALLEL, window_pre=2_000_000, refractory=100_000, seed=42)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.build_random_graph(1); o.init_graph(capi.GRAPH_REFERENCE, 1)
+    assert b.download_synapses().tobytes() == o.download_synapses().tobytes()
+    stim = FunctionalDataset()
+    even = False
+    for p in range(4):
+        vin, exp = stim.nextInput(), stim.nextExpected()
+        for x in (b, o):
+            x.inject_inputs(vin, 1000.0); x.teacher_force(exp, 1.0 if even else 0.0)
+        even = not even
+        sb, so = b.run_pass(1_000_000), o.run_pass(1_000_000)
+        assert sb.events == so.events
+        for f in ("gated", "fired"):
+            g, w = getattr(sb, f), getattr(so, f)
+            assert abs(g - w) <= 0.02 * w + 5 * np.sqrt(w + 1), (p, f, g, w)
+    wb, wo = b.download_synapses()["w"], o.download_synapses()["w"]
+    assert abs(float(wb.mean()) - float(wo.mean())) < 1e-4
+    hb, _ = np.histogram(wb, bins=64, range=(0, 1)); ho, _ = np.histogram(wo, bins=64, range=(0, 1))
+    assert np.abs(hb - ho).sum() / len(wo) < 0.01
+    assert np.array_equal(b.timestamps()[1], o.timestamps()[1])
+
+
+# ---- graph init / I/O ------------------------------------------------------------------------------
+def test_er_beta_init_bit_exact_and_beta_moments():
+    over = dict(n_input=64, n_output=64, n_hidden=100_000, n_syn=500_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.init_graph(capi.GRAPH_ER_BETA, 99); o.init_graph(capi.GRAPH_ER_BETA, 99)
+    s = b.download_synapses()
+    assert s.tobytes() == o.download_synapses().tobytes()
+    assert abs(float(s["w"].mean()) - 0.2) < 2e-3            # Beta(2,8): mean 0.2, var 16/(100*11)
+    assert abs(float(s["w"].var()) - 16 / 1100) < 5e-4
+
+
+def test_bnn_roundtrip_and_shape_error(tmp_path):
+    over = dict(n_input=8, n_output=8, n_hidden=500, n_syn=5000)
+    p = O.default_params(capi.PROFILE_NORTH_STAR, **over)
+    path = str(tmp_path / "model.bnn")
+    with Brain(p) as b:
+        b.build_random_graph(1)
+        want = b.download_synapses()
+        b.save(path)
+    raw = open(path, "rb").read()
+    assert len(raw) == 8 + 16 * 5000 and np.frombuffer(raw[:8], "<u4").tolist() == [5000, 516]   # brain.cpp:161-167
+    with Brain(p) as b:
+        b.load(path)
+        assert b.download_synapses().tobytes() == want.tobytes()
+    q = O.default_params(capi.PROFILE_NORTH_STAR, **dict(over, n_hidden=501))
+    with Brain(q) as b:
+        with pytest.raises(capi.AbnnError) as e:
+            b.load(path)
+        assert e.value.status == capi.ERR_SHAPE                                                  # brain.cpp:174
+
+
+# ---- structural plasticity ---------------------------------------------------------------------------
+def test_prune_compaction_is_stable_and_matches_oracle():
+    rng = np.random.default_rng(3)
+    n, N = 3_000_001, 50_000
+    syn = random_graph(rng, n, N, 0.0, 0.2)
+    over = dict(n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, w_prune=0.05)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.upload_synapses(syn); o.upload_synapses(syn)
+    sb, so = b.prune_and_grow(), o.prune_and_grow()
+    assert (sb.n_before, sb.pruned, sb.n_after) == (so.n_before, so.pruned, so.n_after)
+    got = b.download_synapses()
+    assert got.tobytes() == syn[syn["w"] >= np.float32(0.05)].tobytes()
+    sb2 = b.prune_and_grow()                    # idempotent
+    assert sb2.pruned == 0 and b.download_synapses().tobytes() == got.tobytes()
+
+
+def test_engine_loop_matches_oracle_per_pass_clock():
+    """BrainEngine.run_one_pass order of operations (brain-engine.cpp:108-190) in the reference's own
+    PER_PASS clock with SERIAL execution, 30 passes: filtered read-out bit-exact every pass."""
+    over = dict(n_input=64, n_output=64, n_hidden=2000, n_syn=60_000, exec_mode=capi.EXEC_SERIAL,
+                clock_mode=capi.CLOCK_PER_PASS, window_pre=5, refractory=2, max_spikes_per_pass=2560,
+                reward_window=10)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.build_random_graph(1); o.init_graph(capi.GRAPH_REFERENCE, 1)
+    eng = BrainEngine(b, events_per_pass=60_000, stimulus=FunctionalDataset(64, 64))
+    stim_o = O.Dataset(64, 64)
+    even = False
+    for p in range(30):
+        rb = eng.run_one_pass()
+        vin, exp = stim_o.next_input(), stim_o.next_expected()
+        o.inject_inputs(vin, 1000.0); o.teacher_force(exp, 1.0 if even else 0.0); even = not even
+        o.run_pass(60_000)
+        ro = o.readout_filtered(exp)
+        assert rb.tobytes() == ro.tobytes(), f"pass {p}"
+    assert b.get_loss() == o.get_loss() and o.get_loss()[1] == 3
+    assert_same_state(b, o)
