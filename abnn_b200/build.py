@@ -14,8 +14,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libabnn_b200.so")
-OBJ = os.path.join(HERE, "_obj")
+OUT = os.environ.get("ABNN_B200_OUT") or os.path.join(HERE, "libabnn_b200.so")   # override: tuning variants only
+OBJ = os.path.join(HERE, "_obj" + os.environ.get("ABNN_B200_OBJ_SUFFIX", ""))
 SOURCES = ["traversal.cu", "exact.cu", "io_kernels.cu", "structural.cu", "init.cu", "capi.cu"]
 HOST_SOURCES = ["brain.cpp", "brain_engine.cpp", "manifest.cpp", "engine_capi.cpp"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false",
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not os.path.exists(path):
             continue
         obj = os.path.join(OBJ, src + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("ABNN_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src in HOST_SOURCES:

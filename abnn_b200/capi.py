@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libabnn_b200.so")
+LIB_PATH = os.environ.get("ABNN_B200_LIB") or os.path.join(_HERE, "libabnn_b200.so")   # override: tuning variants only
 
 # ---- enums (include/abnn.h) -------------------------------------------------------------------
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_IO, ERR_SHAPE, ERR_CAPACITY, ERR_COMM, ERR_UNSUPPORTED = (
@@ -52,6 +52,7 @@ class Params(C.Structure):
         ("filter_tau", C.c_double), ("dt_sec", C.c_double), ("loss0", C.c_double),
         ("device", C.c_int32), ("rank", C.c_uint32), ("world_size", C.c_uint32),
         ("l2_persist", C.c_uint32),
+        ("sample_block", C.c_uint32), ("reserved_", C.c_uint32 * 3),
     ]
 
     def copy(self) -> "Params":

@@ -3,6 +3,7 @@
 // sequences the kernels of one pass on the handle's stream (Brain::encode_traversal, brain.cpp:87-122).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -153,6 +154,9 @@ KParams make_kparams(const abnn_handle* h, u64 events)
                            (u64)p.max_spikes_per_pass * p.rank / p.world_size);
     k.grow_cap = h->grow_cap;
     k.seed_lo = (u32)p.seed; k.seed_hi = (u32)(p.seed >> 32);
+    k.sample_block = p.sample_block ? p.sample_block : 1;
+    k.log_block = 0; while ((1u << k.log_block) < k.sample_block) ++k.log_block;
+    k.n_blocks = (h->n_local + k.sample_block - 1) / k.sample_block;
     k.base_scale = p.base_scale; k.a_ltp = p.a_ltp; k.a_ltd = p.a_ltd; k.w_min = p.w_min; k.w_max = p.w_max;
     k.eta_home = p.eta_home; k.target_rate_hz = p.target_rate_hz; k.home_tick_hz = p.home_tick_hz;
     k.eta_reward = p.eta_reward; k.alpha_rbar = p.alpha_rbar; k.p_new = p.p_new;
@@ -265,6 +269,7 @@ int abnn_default_params(abnn_params* p, uint32_t profile)
     p->use_fir = 1; p->fir_size = 20; p->reward_window = 1000;
     p->filter_tau = 0.02; p->dt_sec = 0.0009; p->loss0 = 0.25;
     p->device = -1; p->rank = 0; p->world_size = 1; p->l2_persist = 1;
+    p->sample_block = 1;
     return 0;
 }
 
@@ -300,6 +305,8 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (!p.world_size || p.rank >= p.world_size) return fail(ABNN_ERR_INVALID, "bad rank/world_size");
     if (p.sampler > 1 || p.release_rng > 1 || p.clock_mode > 1 || p.exec_mode > 2 || p.src_view > 1 || p.rbar_mode > 1)
         return fail(ABNN_ERR_INVALID, "unknown mode value");
+    if (p.sample_block > 32 || (p.sample_block & (p.sample_block - 1)))
+        return fail(ABNN_ERR_INVALID, "sample_block must be a power of two <= 32 (0 = 1)");
     if (!p.n_output || p.fir_size == 0 || p.fir_size > ABNN_MAX_FIR) return fail(ABNN_ERR_INVALID, "bad n_output / fir_size");
     const u64 N = (u64)p.n_input + p.n_output + p.n_hidden;
     if (N >= (1ull << 32)) return fail(ABNN_ERR_INVALID, "neuron ids are 32-bit (SynapsePacked.src/dst)");
@@ -319,6 +326,12 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (dev < 0) CU(cudaGetDevice(&dev));
     if (dev >= ndev) return fail(ABNN_ERR_INVALID, "device ordinal out of range");
     CU(cudaSetDevice(dev));
+
+    // Random 16-byte gathers and 8-byte timestamp accesses use ONE 32-byte sector each; with the default
+    // L2 fetch granularity every miss pulls 128 B from HBM (measured: 213 B of DRAM reads per event,
+    // profiles/r1_ncu_summary.md). Ask for sector-sized fetches (device-wide hint).
+    if (!getenv("ABNN_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();
 
     abnn_handle* h = new abnn_handle;
     h->p = p; h->device = dev; h->N = N;

@@ -96,6 +96,8 @@ struct KParams {
     u32 budget_share;    // this rank's share of max_spikes_per_pass
     u32 grow_cap;
     u32 seed_lo, seed_hi;
+    u32 sample_block, log_block;   // PHILOX sampler granularity (power of two)
+    u64 n_blocks;                  // ceil(n_local / sample_block)
     float base_scale, a_ltp, a_ltd, w_min, w_max, eta_home, target_rate_hz, home_tick_hz, eta_reward, alpha_rbar;
     float p_new;
 };

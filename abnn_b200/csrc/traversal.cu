@@ -13,6 +13,8 @@
 //   k_traverse_serial   : one thread walks the events in index order (the bit-exact order of the
 //                         oracle). Reference for the EXACT mode and the parity tests.
 //   k_end_pass          : r-bar step, clock advance, counters -> stats slot (no host round trip).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -73,7 +75,14 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
         if (need_philox) r = event_philox(kp, eid);
         u64 edge;
         if (kp.sampler == ABNN_SAMPLER_SWEEP) { edge = i; if (edge >= kp.n_local) continue; }
-        else { if (!kp.n_local) break; edge = mulhi64(((u64)r.x << 32) | r.y, kp.n_local); }
+        else if (kp.sample_block == 1) { if (!kp.n_local) break; edge = mulhi64(((u64)r.x << 32) | r.y, kp.n_local); }
+        else {
+            if (!kp.n_local) break;
+            const u64 lane = i & (kp.sample_block - 1);
+            const Philox4 q = event_philox(kp, eid - lane);
+            edge = (mulhi64(((u64)q.x << 32) | q.y, kp.n_blocks) << kp.log_block) + lane;
+            if (edge >= kp.n_local) continue;
+        }
         const u64 now = event_now(kp, clock, i);
         const abnn_synapse s = d.syn[edge];
         if (kp.track_visits && d.visited[s.dst] < now) d.visited[s.dst] = now;
@@ -102,65 +111,102 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
 }
 
 // ================================================================================================
-// PARALLEL rare path: the event passed the pre-spike window. Lanes of the warp that hit the same
-// destination are serialised in lane (= event) order; everything else proceeds concurrently.
-__device__ __noinline__ void rare_path(const KParams& kp, const DevPtrs& d, u64 i, u64 edge, u32 src, u32 dst,
-                                       float w_loaded, u64 now)
+// PARALLEL execution.
+//
+// Hot part (every event): gather the SynapsePacked record, read lastFired[src] from the pass-start
+// view (one L2 sector), RED.MAX.64 lastVisited[dst] (one L2 sector), test the pre-spike window.
+// Gated path (events that pass the window, brain.metal:74): lanes of the warp that hit the same
+// destination are serialised in lane (= event) order with match.any; timestamps move with 64-bit
+// atomicMax, so "the latest event wins" holds whatever the execution order.
+// (A variant that queued candidates in shared memory and processed them 32 at a time was measured
+// slower — the kernel is bound by L2 sector operations and latency, not by issue slots; see
+// profiles/r1_ncu_summary.md.)
+struct PassConsts { u64 clock, event_base, tick_base; float R, rbar; };
+
+// One candidate's turn: refractory + budget gates, release test, plasticity, timestamp write.
+// Returns bit0 = gated (weight written), bit1 = fired.
+__device__ __forceinline__ u32 candidate_turn(const KParams& kp, const DevPtrs& d, const PassConsts& pc, u64 i, u64 edge,
+                                              u32 src, u32 dst, float w, u64 now, bool reload_w)
+{
+    const u64 ld = __ldcg(d.live + dst);
+    if (now - ld <= kp.refractory) return 0;                                               // brain.metal:79-83
+    if (kp.budget_on && *(volatile u32*)&d.sc->fires_claimed >= kp.budget_share) return 0;  // brain.metal:85-88
+    if (reload_w) w = __ldcg(&d.syn[edge].w);        // an earlier same-destination peer may have updated this record
+    const u64 eid = pc.event_base + i;
+    Philox4 r{0, 0, 0, 0};
+    if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_philox(kp, eid);
+    const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
+    bool fired = release_test(kp, w, u);
+    if (fired && kp.budget_on) {                                                            // brain.metal:95-98, saturating
+        const u32 old = atomicAdd(&d.sc->fires_claimed, 1u);
+        if (old >= kp.budget_share) { fired = false; atomicSub(&d.sc->fires_claimed, 1u); }
+    }
+    __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, now, ld));               // brain.metal:122
+    if (!fired) return 1;
+    atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
+    stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.w);
+    return 3;
+}
+
+__device__ __forceinline__ u32 gated_path(const KParams& kp, const DevPtrs& d, const PassConsts& pc, u64 i, u64 edge,
+                                          u32 src, u32 dst, float w_loaded, u64 now)
 {
     const unsigned act   = __activemask();
     const unsigned peers = __match_any_sync(act, dst);
-    const int my_turn    = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
-    const int turns      = __reduce_max_sync(act, __popc(peers));
-    DevScalars* sc = d.sc;
-    const float R = sc->reward, rbar = sc->rbar;        // constant during a pass (PASS_STEP r-bar)
-    bool gated = false, fired = false;
-    for (int t = 0; t < turns; ++t) {
-        if (t == my_turn) {
-            const u64 ld = *(volatile u64*)(d.live + dst);
-            bool pass = !(now - ld <= kp.refractory);                                       // brain.metal:79-83
-            if (pass && kp.budget_on && *(volatile u32*)&sc->fires_claimed >= kp.budget_share) pass = false;   // :85-88
-            if (pass) {
-                const float w0 = t == 0 ? w_loaded : *(volatile float*)&d.syn[edge].w;      // same-edge peers see the update
-                const u64 eid = sc->event_base + i;
-                Philox4 r{0, 0, 0, 0};
-                if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_philox(kp, eid);
-                const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
-                fired = release_test(kp, w0, u);
-                if (fired && kp.budget_on) {                                                // brain.metal:95-98, saturating
-                    const u32 old = atomicAdd(&sc->fires_claimed, 1u);
-                    if (old >= kp.budget_share) { fired = false; atomicSub(&sc->fires_claimed, 1u); }
-                }
-                const float w1 = plasticity(kp, w0, fired, R, rbar, now, ld);
-                *(volatile float*)&d.syn[edge].w = w1;                                      // brain.metal:122
-                gated = true;
-                if (fired) {
-                    atomicMax(d.live + dst, now);                                           // brain.metal:125-126
-                    stage_growth(kp, d, eid, sc->tick_base + i * kp.world + kp.rank, src, r.w);
-                }
-            }
-        }
-        __syncwarp(act);
+    const unsigned lane  = threadIdx.x & 31;
+    const unsigned conflicted = __ballot_sync(act, peers != (1u << lane));   // lanes that share a destination
+    if (peers == (1u << lane))                                               // common case: destination unique in the warp
+        return candidate_turn(kp, d, pc, i, edge, src, dst, w_loaded, now, false);
+    const int my_turn = __popc(peers & ((1u << lane) - 1u));
+    const int turns = __reduce_max_sync(conflicted, __popc(peers));
+    u32 result = 0;
+    for (int t = 0; t < turns; ++t) {                                        // one turn each, in lane order
+        if (t == my_turn) result = candidate_turn(kp, d, pc, i, edge, src, dst, w_loaded, now, t > 0);
+        __syncwarp(conflicted);
     }
-    const unsigned ng = __popc(__ballot_sync(act, gated)), nf = __popc(__ballot_sync(act, fired)), nc = __popc(act);
-    if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) {
-        atomicAdd(&sc->cands, (u64)nc);
-        if (ng) atomicAdd(&sc->gated, (u64)ng);
-        if (nf) atomicAdd(&sc->fired, (u64)nf);
+    return result;
+}
+
+__device__ __forceinline__ void flush_counters(const DevPtrs& d, u32 n_cand, u32 n_gated, u32 n_fired, u32* s_cnt)
+{
+    n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+    n_gated = __reduce_add_sync(0xffffffffu, n_gated);
+    n_fired = __reduce_add_sync(0xffffffffu, n_fired);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_cand) atomicAdd(&s_cnt[0], n_cand);
+        if (n_gated) atomicAdd(&s_cnt[1], n_gated);
+        if (n_fired) atomicAdd(&s_cnt[2], n_fired);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&d.sc->cands, (u64)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&d.sc->gated, (u64)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&d.sc->fired, (u64)s_cnt[2]);
     }
 }
 
-// 16-byte streaming gather of one SynapsePacked: L1 no-allocate, evict-first in L2 so the synapse
-// stream does not displace the timestamp arrays (which are pinned with an access-policy window).
+// 16-byte streaming gather of one SynapsePacked (evict-first: the synapse stream should not displace
+// the timestamp arrays in L2).
 __device__ __forceinline__ uint4 load_synapse(const abnn_synapse* p)
 {
     return __ldcs(reinterpret_cast<const uint4*>(p));
 }
 
-// PARALLEL: each CTA walks tiles of 256*U events; a thread keeps U independent gathers in flight.
+#ifndef ABNN_TRAV_MIN_CTAS
+#define ABNN_TRAV_MIN_CTAS 3
+#endif
+
+// iid PHILOX sampler (sample_block = 1) and SWEEP sampler: each CTA walks tiles of 256*U events; a
+// thread keeps U independent gathers in flight. Pass counters stay in registers and are reduced once
+// per CTA (no per-event global atomics).
 template <int SAMPLER, int VISITS, int U>
-__global__ void __launch_bounds__(256) k_traverse_parallel(const __grid_constant__ KParams kp, const DevPtrs d)
+__global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(const __grid_constant__ KParams kp, const DevPtrs d)
 {
-    const u64 clock = d.sc->clock, event_base = d.sc->event_base;
+    __shared__ u32 s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const PassConsts pc{d.sc->clock, d.sc->event_base, d.sc->tick_base, d.sc->reward, d.sc->rbar};
+    u32 n_cand = 0, n_gated = 0, n_fired = 0;
     const u64 tile = 256ull * U;
     for (u64 base = (u64)blockIdx.x * tile; base < kp.count; base += (u64)gridDim.x * tile) {
         u64   edge[U];
@@ -172,7 +218,7 @@ __global__ void __launch_bounds__(256) k_traverse_parallel(const __grid_constant
             const u64 i = base + (u64)j * 256 + threadIdx.x;
             ok[j] = i < kp.count;
             if (SAMPLER == ABNN_SAMPLER_PHILOX) {
-                const Philox4 r = event_philox(kp, event_base + i);
+                const Philox4 r = event_philox(kp, pc.event_base + i);
                 edge[j] = mulhi64(((u64)r.x << 32) | r.y, kp.n_local);
             } else {
                 edge[j] = i;
@@ -189,12 +235,76 @@ __global__ void __launch_bounds__(256) k_traverse_parallel(const __grid_constant
         for (int j = 0; j < U; ++j) {
             if (!ok[j]) continue;
             const u64 i = base + (u64)j * 256 + threadIdx.x;
-            const u64 now = event_now(kp, clock, i);
+            const u64 now = event_now(kp, pc.clock, i);
             if (VISITS) atomicMax(d.visited + s[j].y, now);                      // README.md:84 (RED.MAX.64 at L2)
-            if (now - lp[j] <= kp.window_pre)                                    // brain.metal:74
-                rare_path(kp, d, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
+            if (now - lp[j] <= kp.window_pre) {                                  // brain.metal:74
+                const u32 r = gated_path(kp, d, pc, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
+                ++n_cand; n_gated += r & 1u; n_fired += r >> 1;
+            }
         }
     }
+    flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
+}
+
+// Block sampler (sample_block = B = 2^LOGB > 1): one Philox draw selects a block-aligned run of B
+// consecutive SynapsePacked records and B consecutive events process it. With B = 8 a draw is exactly
+// one 128-byte HBM line — the unit B200 fetches on every L2 miss whatever the load asks for — so all 8
+// records of a fetched line do work instead of 1 (profiles/r1_probe_gather.md).
+// A warp owns chunks of 32 groups: lane L draws the block of group L, then in iteration k the warp
+// processes groups k*(32/B).. with B lanes per group reading the B records (coalesced: one line per B
+// lanes); the block base travels by shuffle. One Philox per B events instead of one per event.
+template <int LOGB, int VISITS>
+__global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(const __grid_constant__ KParams kp, const DevPtrs d)
+{
+    constexpr int B = 1 << LOGB;
+    constexpr int GPI = 32 / B;            // groups served per warp iteration
+    constexpr int KB = B < 4 ? B : 4;      // iterations batched for memory-level parallelism
+    __shared__ u32 s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const PassConsts pc{d.sc->clock, d.sc->event_base, d.sc->tick_base, d.sc->reward, d.sc->rbar};
+    u32 n_cand = 0, n_gated = 0, n_fired = 0;
+    const unsigned lane = threadIdx.x & 31;
+    const u32 rec = lane & (B - 1);
+    const u64 warps_total = (u64)gridDim.x * 8, warp_global = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const u64 n_chunks = (kp.count + 32ull * B - 1) / (32ull * B);
+    for (u64 c = warp_global; c < n_chunks; c += warps_total) {
+        const u64 i0 = (c * 32 + lane) << LOGB;                  // first event of this lane's group
+        u64 be = ~0ull;
+        if (i0 < kp.count) {
+            const Philox4 r = event_philox(kp, pc.event_base + i0);
+            be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGB;
+        }
+#pragma unroll
+        for (int k0 = 0; k0 < B; k0 += KB) {
+            u64   ev[KB], ed[KB], lp[KB];
+            uint4 s[KB];
+            bool  ok[KB];
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) {
+                const int src_lane = (k0 + kk) * GPI + (int)(lane >> LOGB);
+                const u64 b = __shfl_sync(0xffffffffu, be, src_lane);
+                ev[kk] = ((c * 32 + src_lane) << LOGB) + rec;
+                ed[kk] = b + rec;
+                ok[kk] = b != ~0ull && ev[kk] < kp.count && ed[kk] < kp.n_local;
+                if (ok[kk]) s[kk] = load_synapse(d.syn + ed[kk]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk)
+                if (ok[kk]) lp[kk] = __ldcg(d.view + s[kk].x);
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) {
+                if (!ok[kk]) continue;
+                const u64 now = event_now(kp, pc.clock, ev[kk]);
+                if (VISITS) atomicMax(d.visited + s[kk].y, now);
+                if (now - lp[kk] <= kp.window_pre) {
+                    const u32 r = gated_path(kp, d, pc, ev[kk], ed[kk], s[kk].x, s[kk].y, __uint_as_float(s[kk].z), now);
+                    ++n_cand; n_gated += r & 1u; n_fired += r >> 1;
+                }
+            }
+        }
+    }
+    flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
 }
 
 // End of pass: r-bar EWMA (once per pass), clock (brain.metal:129 / README.md:85),
@@ -214,24 +324,65 @@ __global__ void k_end_pass(const __grid_constant__ KParams kp, DevScalars* sc, a
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
-template <int SAMPLER, int VISITS>
-static cudaError_t launch_parallel_t(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
+template <int SAMPLER, int VISITS, int U>
+static cudaError_t launch_parallel_u(const KParams& kp, const DevPtrs& d, int sm_count, int per_sm_req, cudaStream_t st)
 {
-    constexpr int U = 4;
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_parallel<SAMPLER, VISITS, U>, 256, 0);
     if (per_sm < 1) per_sm = 1;
-    const u64 tiles = (kp.count + 256ull * U - 1) / (256ull * U);
+    if (per_sm_req > 0 && per_sm_req < per_sm) per_sm = per_sm_req;
+    const u64 tiles = (kp.count + 256ull * U - 1) / (256ull * U);   // 8 warps x 32*U events
     u64 grid = (u64)sm_count * per_sm;                 // persistent: a whole number of waves
     if (grid > tiles) grid = tiles;
     if (grid == 0) return cudaSuccess;
     k_traverse_parallel<SAMPLER, VISITS, U><<<(unsigned)grid, 256, 0, st>>>(kp, d);
     return cudaGetLastError();
 }
+template <int SAMPLER, int VISITS>
+static cudaError_t launch_parallel_t(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
+{
+    // tuning knobs (read once): events in flight per thread, CTAs per SM
+    static const int u = getenv("ABNN_TRAV_U") ? atoi(getenv("ABNN_TRAV_U")) : 4;
+    static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
+    switch (u) {
+        case 1:  return launch_parallel_u<SAMPLER, VISITS, 1>(kp, d, sm_count, bps, st);
+        case 2:  return launch_parallel_u<SAMPLER, VISITS, 2>(kp, d, sm_count, bps, st);
+        case 8:  return launch_parallel_u<SAMPLER, VISITS, 8>(kp, d, sm_count, bps, st);
+        default: return launch_parallel_u<SAMPLER, VISITS, 4>(kp, d, sm_count, bps, st);
+    }
+}
+
+template <int LOGB, int VISITS>
+static cudaError_t launch_block_t(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
+{
+    static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_block<LOGB, VISITS>, 256, 0);
+    if (per_sm < 1) per_sm = 1;
+    if (bps > 0 && bps < per_sm) per_sm = bps;
+    const u64 chunks = (kp.count + (32ull << LOGB) - 1) / (32ull << LOGB);
+    u64 grid = (u64)sm_count * per_sm;
+    if (grid > (chunks + 7) / 8) grid = (chunks + 7) / 8;
+    if (grid == 0) return cudaSuccess;
+    k_traverse_block<LOGB, VISITS><<<(unsigned)grid, 256, 0, st>>>(kp, d);
+    return cudaGetLastError();
+}
+template <int VISITS>
+static cudaError_t launch_block(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
+{
+    switch (kp.log_block) {
+        case 1:  return launch_block_t<1, VISITS>(kp, d, sm_count, st);
+        case 2:  return launch_block_t<2, VISITS>(kp, d, sm_count, st);
+        case 3:  return launch_block_t<3, VISITS>(kp, d, sm_count, st);
+        case 4:  return launch_block_t<4, VISITS>(kp, d, sm_count, st);
+        default: return launch_block_t<5, VISITS>(kp, d, sm_count, st);
+    }
+}
 
 cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     const bool ph = kp.sampler == ABNN_SAMPLER_PHILOX, vis = kp.track_visits != 0;
+    if (ph && kp.sample_block > 1) return vis ? launch_block<1>(kp, d, sm_count, st) : launch_block<0>(kp, d, sm_count, st);
     if (ph && vis)  return launch_parallel_t<ABNN_SAMPLER_PHILOX, 1>(kp, d, sm_count, st);
     if (ph && !vis) return launch_parallel_t<ABNN_SAMPLER_PHILOX, 0>(kp, d, sm_count, st);
     if (!ph && vis) return launch_parallel_t<ABNN_SAMPLER_SWEEP, 1>(kp, d, sm_count, st);

@@ -49,8 +49,10 @@ def parse():
     ap.add_argument("--syn", type=int, default=1_000_000_000)
     ap.add_argument("--events", type=int, default=150_000_000)
     ap.add_argument("--sampler", default="philox", choices=["philox", "sweep"])
+    ap.add_argument("--block", type=int, default=8, help="PHILOX sampler granularity in records (8 = one 128-byte HBM line per draw; 1 = iid)")
     ap.add_argument("--warm-frac", type=float, default=0.25,
                     help="fraction of neurons whose lastFired is pre-seeded inside the pre-spike window (SURVEY §8d 'warm' variant)")
+    ap.add_argument("--src-view", default="snapshot", choices=["snapshot", "live"])
     ap.add_argument("--no-visits", action="store_true")
     ap.add_argument("--no-l2-persist", action="store_true")
     ap.add_argument("--cpu-syn", type=int, default=100_000_000)
@@ -129,7 +131,8 @@ def base_params(args, O, capi, rank, world, events):
                 sampler=capi.SAMPLER_PHILOX if args.sampler == "philox" else capi.SAMPLER_SWEEP,
                 exec_mode=capi.EXEC_PARALLEL, window_pre=5 * events, refractory=2 * events,
                 track_visits=0 if args.no_visits else 1, l2_persist=0 if args.no_l2_persist else 1,
-                rank=rank, world_size=world, device=-1)
+                rank=rank, world_size=world, device=-1, sample_block=args.block,
+                src_view=capi.SRC_SNAPSHOT if args.src_view == "snapshot" else capi.SRC_LIVE)
     return O.default_params(capi.PROFILE_NORTH_STAR, **over)
 
 
@@ -307,7 +310,7 @@ def main():
             "metric": "synaptic events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64 timestamps + f32 weights", "data": "synthetic",
-            "config": {"workload": workload, "sampler": args.sampler, "exec_mode": "parallel", "clock": "per_event",
+            "config": {"workload": workload, "sampler": args.sampler, "sample_block": args.block, "exec_mode": "parallel", "clock": "per_event",
                        "graph": "ER endpoints, Beta(2,8) weights (Philox)", "window_pre_passes": 5, "refractory_passes": 2,
                        "warm_fraction": args.warm_frac, "track_visits": not args.no_visits,
                        "parallelism": f"dst-shard x{world}" if world > 1 else "single GPU",

@@ -146,6 +146,15 @@ typedef struct abnn_params {
     uint32_t rank;                 /* 0 .. world_size-1                                         */
     uint32_t world_size;           /* 1 = single GPU                                            */
     uint32_t l2_persist;           /* 1: pin the timestamp arrays in L2 with an access-policy window */
+
+    /* PHILOX sampler granularity: events are drawn in groups of sample_block consecutive events that
+     * process sample_block consecutive table records starting at a Philox-chosen, block-aligned
+     * position: edge(i) = B*mulhi64(philox(seed, i - i%B).xy, ceil(n/B)) + i%B  (skipped if >= n).
+     * 1 = every event draws its own edge (README.md:77). 8 = one 128-byte HBM line per draw (B200's
+     * DRAM fetch granularity: a random 16-byte gather costs a whole line, profiles/r1_probe_gather.md).
+     * Power of two, <= 32. Every edge is still sampled with equal probability. */
+    uint32_t sample_block;
+    uint32_t reserved_[3];
 } abnn_params;
 
 #define ABNN_MAX_FIR 64u

@@ -133,7 +133,13 @@ ob_handle* ob_create(const abnn_params* p)
     ob_partition(h->N, p->world_size, p->rank, &h->lo, &h->hi);
     h->live.assign(h->N, 0); h->view.assign(h->N, 0); h->lastV.assign(h->N, 0);
     h->n_local_all.assign(p->world_size, 0);
+    // capacity rule of the C-ABI (include/abnn.h: syn_capacity 0 = this rank's share of n_syn, plus slack when sharded)
     h->cap = p->syn_capacity;
+    if (!h->cap)
+        h->cap = p->world_size == 1 ? p->n_syn
+                                    : (p->n_syn + p->world_size - 1) / p->world_size + p->n_syn / (16ull * p->world_size) +
+                                          65536 + uint64_t(p->n_input) * p->n_output;
+    if (!h->cap) h->cap = 1;
     h->max_observed = p->peak_init;
     h->last_loss = p->loss0;
     h->rate.assign(p->n_output, 0.f);
@@ -155,7 +161,7 @@ int ob_upload_synapses(ob_handle* h, const abnn_synapse* s, uint64_t n)
     h->syn.clear();
     for (uint64_t i = 0; i < n; ++i)
         if (s[i].dst >= h->lo && s[i].dst < h->hi) h->syn.push_back(s[i]);
-    if (h->cap && h->syn.size() > h->cap) return ABNN_ERR_CAPACITY;
+    if (h->syn.size() > h->cap) return ABNN_ERR_CAPACITY;
     recount(h);
     return 0;
 }
@@ -295,6 +301,7 @@ int ob_run_pass(ob_handle* h, uint64_t events, abnn_pass_stats* st)
     }
     (void)first;
     const uint64_t n_local = h->syn.size();
+    const uint64_t B = p.sample_block ? p.sample_block : 1;
     const bool budget_on = p.max_spikes_per_pass != 0;
     uint64_t fires_left = budget_on
         ? (uint64_t(p.max_spikes_per_pass) * (k + 1) / G - uint64_t(p.max_spikes_per_pass) * k / G) : 0;   // brain.cpp:90
@@ -311,7 +318,16 @@ int ob_run_pass(ob_handle* h, uint64_t events, abnn_pass_stats* st)
             philox4x32_10(uint32_t(eid), uint32_t(eid >> 32), k, STREAM_EVENT, uint32_t(p.seed), uint32_t(p.seed >> 32), r);
         uint64_t edge;
         if (p.sampler == ABNN_SAMPLER_SWEEP) { edge = i; if (edge >= n_local) continue; }   // brain.metal:60-61
-        else { if (!n_local) break; edge = mulhi64((uint64_t(r[0]) << 32) | r[1], n_local); }
+        else if (B == 1) { if (!n_local) break; edge = mulhi64((uint64_t(r[0]) << 32) | r[1], n_local); }
+        else {
+            // block sampler (include/abnn.h sample_block): the group's first event draws the block
+            if (!n_local) break;
+            const uint64_t lane = i % B, eid0 = eid - lane;
+            uint32_t q[4];
+            philox4x32_10(uint32_t(eid0), uint32_t(eid0 >> 32), k, STREAM_EVENT, uint32_t(p.seed), uint32_t(p.seed >> 32), q);
+            edge = B * mulhi64((uint64_t(q[0]) << 32) | q[1], (n_local + B - 1) / B) + lane;
+            if (edge >= n_local) continue;
+        }
         // K2: clock
         const uint64_t now = p.clock_mode == ABNN_CLOCK_PER_PASS ? h->clock : h->clock + i * G + k;
         abnn_synapse s = h->syn[edge];                           // brain.metal:70
@@ -455,7 +471,7 @@ uint64_t ob_grow_apply(ob_handle* h, const void* cands, uint64_t n, uint64_t* dr
     uint64_t app = 0, drop = 0;
     for (const auto& g : c) {
         if (g.dst < h->lo || g.dst >= h->hi) continue;
-        if (h->cap && h->syn.size() >= h->cap) { ++drop; continue; }
+        if (h->syn.size() >= h->cap) { ++drop; continue; }
         h->syn.push_back(abnn_synapse{g.src, g.dst, h->p.w_init, 0.f});
         ++app;
     }
