@@ -1,0 +1,133 @@
+"""Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi`):
+two ranks, one process and one GPU each, NCCL allgather of lastFired slices inside the library,
+against the single-process OracleWorld(2) — bit-exact in SERIAL execution, including the structural
+step (local prune-compaction, allgathered growth candidates appended in event order)."""
+import socket
+
+import numpy as np
+import pytest
+
+from abnn_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+SCEN = dict(n_input=16, n_output=16, n_hidden=30_001, n_syn=400_000, window_pre=2_000_000, refractory=300_000,
+            p_new=0.2, w_prune=0.05, syn_capacity=300_000, sample_block=8)
+
+
+def _inputs():
+    rng = np.random.default_rng(4)
+    N = 16 + 16 + SCEN["n_hidden"]
+    n = SCEN["n_syn"]
+    from oracle.pyoracle import SYN_DTYPE
+    syn = np.zeros(n, SYN_DTYPE)
+    syn["src"] = rng.integers(0, N, n); syn["dst"] = rng.integers(0, N, n)
+    syn["w"] = rng.uniform(0.02, 1.0, n).astype(np.float32)
+    pre = rng.integers(1, 500_000, N).astype(np.uint64)
+    frames = [(rng.random(16).astype(np.float32), rng.random(16).astype(np.float32)) for _ in range(4)]
+    return N, syn, pre, frames
+
+
+def _gpu_worker(rank, world, port, exec_mode, q):
+    import torch
+    import torch.distributed as dist
+    from abnn_b200 import distributed as D
+    from oracle import pyoracle as O
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        base = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=exec_mode, **SCEN)
+        b = D.create_sharded_brain(base, device=rank)
+        N, syn, pre, frames = _inputs()
+        b.upload_synapses(syn)
+        b.upload_timestamps(pre, None); b.clock = 500_000; b.set_reward(0.2)
+        stats = []
+        for it, (vin, exp) in enumerate(frames):
+            b.inject_inputs(vin, 1000.0); b.teacher_force(exp, float(it & 1))
+            st = b.run_pass(300_000)
+            stats.append((st.events, st.gated, st.fired, st.grown))
+            if it == 1:
+                ss = b.prune_and_grow()
+                stats.append((ss.pruned, ss.appended, ss.n_after, ss.dropped))
+        info = b.info()
+        lf, lv = b.timestamps()
+        q.put((rank, stats, b.download_synapses().tobytes(), lf.tobytes(), lv[info.neuron_lo:info.neuron_hi].tobytes(),
+               b.clock, info.n_syn_global, b.read_outputs().tobytes()))
+        b.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_gpu(exec_mode):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, exec_mode, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in procs])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    return res
+
+
+def _run_oracle():
+    from oracle import pyoracle as O
+    base = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_SERIAL, **SCEN)
+    world = O.OracleWorld(base, 2)
+    N, syn, pre, frames = _inputs()
+    world.upload_synapses(syn)
+    for s in world.shards:
+        s.upload_timestamps(pre, None); s.clock = 500_000; s.set_reward(0.2)
+    per_rank = [[], []]
+    for it, (vin, exp) in enumerate(frames):
+        for s in world.shards:
+            s.inject_inputs(vin, 1000.0); s.teacher_force(exp, float(it & 1))
+        sts = [s.run_pass(300_000) for s in world.shards]
+        half = -(-N // 2)
+        for k, s in enumerate(world.shards):
+            live, _ = s.live_view()
+            for t in world.shards:
+                t.live_view()[1][k * half:min(N, (k + 1) * half)] = live[k * half:min(N, (k + 1) * half)]
+            per_rank[k].append((sts[k].events, sts[k].gated, sts[k].fired, sts[k].grown))
+        if it == 1:
+            before = [s.n_syn_local() for s in world.shards]
+            pruned = [s.prune() for s in world.shards]
+            allc = np.concatenate([s.grow_fetch() for s in world.shards])
+            for k, s in enumerate(world.shards):
+                app, drop = s.grow_apply(allc)
+                per_rank[k].append((pruned[k], app, before[k] - pruned[k] + app, drop))
+            world._sync_counts()
+    return world, per_rank, N
+
+
+def test_two_gpus_serial_bit_exact():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run_gpu(capi.EXEC_SERIAL)
+    world, per_rank, N = _run_oracle()
+    half = -(-N // 2)
+    for k, s in enumerate(world.shards):
+        rank, stats, syn_b, lf_b, lv_b, clock, n_global, outs = res[k]
+        assert stats == per_rank[k], (k, stats, per_rank[k])
+        assert syn_b == s.download_synapses().tobytes()
+        assert lf_b == s.live_view()[1].tobytes()                      # replicated view after the last exchange
+        assert lv_b == s.timestamps()[1][k * half:min(N, (k + 1) * half)].tobytes()
+        assert clock == s.clock
+        assert n_global == sum(t.n_syn_local() for t in world.shards)
+        assert outs == s.read_outputs().tobytes()
+    assert sum(x[1] for x in per_rank[0][:2]) > 1000
+
+
+def test_two_gpus_parallel_statistical():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run_gpu(capi.EXEC_PARALLEL)
+    world, per_rank, N = _run_oracle()
+    for k in range(2):
+        stats = res[k][1]
+        for a, b in zip(stats, per_rank[k]):
+            if len(a) == 4 and a[0] == b[0] and a[0] > 10_000:       # pass statistics rows (events equal)
+                assert abs(a[1] - b[1]) <= 0.08 * b[1] + 50 and abs(a[2] - b[2]) <= 0.1 * b[2] + 50, (k, a, b)
