@@ -28,11 +28,11 @@ __device__ __forceinline__ bool release_test(const KParams& kp, float w, float u
     const float p = clampf(w * w * kp.base_scale, 0.f, 1.f);     // brain.metal:91
     return p > u;                                                // brain.metal:92
 }
-__device__ __forceinline__ float plasticity(const KParams& kp, float w, bool fired, float R, float rbar, u64 now, u64 ld)
+__device__ __forceinline__ float plasticity(const KParams& kp, float w, bool fired, float R, float rbar, u64 isi_ticks)
 {
     float dW = fired ? (kp.a_ltp * (1.f - w)) : (-kp.a_ltd * w);              // brain.metal:101-102
     dW += kp.eta_reward * (R - rbar) * (fired ? 1.0f : 0.0f);                 // brain.metal:107
-    const float isi = (float)(now - ld);                                      // brain.metal:116
+    const float isi = (float)isi_ticks;                                       // brain.metal:116 (now - ld)
     const float est = isi > 0.f ? kp.home_tick_hz / isi : 0.f;                // brain.metal:117
     dW += kp.eta_home * (kp.target_rate_hz - est) * w;                        // brain.metal:118
     return clampf(w + dW, kp.w_min, kp.w_max);                                // brain.metal:121
@@ -95,7 +95,7 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
         const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
         const bool fired = release_test(kp, s.w, u);
         if (fired) ++fires;
-        const float w = plasticity(kp, s.w, fired, R, rbar, now, ld);
+        const float w = plasticity(kp, s.w, fired, R, rbar, now - ld);
         if (kp.rbar_mode == ABNN_RBAR_METAL_TID0 && i == 0 && kp.rank == 0)
             rbar = rbar + kp.alpha_rbar * (R - rbar);                         // brain.metal:110-113
         d.syn[edge].w = w;                                                    // brain.metal:122
@@ -128,8 +128,12 @@ struct PassConsts { u64 clock, event_base, tick_base; float R, rbar; };
 __device__ __forceinline__ u32 candidate_turn(const KParams& kp, const DevPtrs& d, const PassConsts& pc, u64 i, u64 edge,
                                               u32 src, u32 dst, float w, u64 now, bool reload_w)
 {
+    // Unordered execution can observe a fire that is LATER than this event (ld > now); the unsigned
+    // difference would wrap and look ancient. The gate is therefore symmetric: two fires of one neuron
+    // are never closer than the refractory period. In event order ld <= now and this is brain.metal:79-83.
     const u64 ld = __ldcg(d.live + dst);
-    if (now - ld <= kp.refractory) return 0;                                               // brain.metal:79-83
+    const u64 gap = ld <= now ? now - ld : ld - now;
+    if (gap <= kp.refractory) return 0;                                                    // brain.metal:79-83
     if (kp.budget_on && *(volatile u32*)&d.sc->fires_claimed >= kp.budget_share) return 0;  // brain.metal:85-88
     if (reload_w) w = __ldcg(&d.syn[edge].w);        // an earlier same-destination peer may have updated this record
     const u64 eid = pc.event_base + i;
@@ -141,7 +145,7 @@ __device__ __forceinline__ u32 candidate_turn(const KParams& kp, const DevPtrs& 
         const u32 old = atomicAdd(&d.sc->fires_claimed, 1u);
         if (old >= kp.budget_share) { fired = false; atomicSub(&d.sc->fires_claimed, 1u); }
     }
-    __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, now, ld));               // brain.metal:122
+    __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, gap));                   // brain.metal:122
     if (!fired) return 1;
     atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
     stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.w);
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
             const u64 i = base + (u64)j * 256 + threadIdx.x;
             const u64 now = event_now(kp, pc.clock, i);
             if (VISITS) atomicMax(d.visited + s[j].y, now);                      // README.md:84 (RED.MAX.64 at L2)
-            if (now - lp[j] <= kp.window_pre) {                                  // brain.metal:74
+            if (now - lp[j] <= kp.window_pre || (!kp.snapshot && lp[j] > now)) { // brain.metal:74 (live view: a later spike is recent)
                 const u32 r = gated_path(kp, d, pc, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
                 ++n_cand; n_gated += r & 1u; n_fired += r >> 1;
             }
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
                 if (!ok[kk]) continue;
                 const u64 now = event_now(kp, pc.clock, ev[kk]);
                 if (VISITS) atomicMax(d.visited + s[kk].y, now);
-                if (now - lp[kk] <= kp.window_pre) {
+                if (now - lp[kk] <= kp.window_pre || (!kp.snapshot && lp[kk] > now)) {
                     const u32 r = gated_path(kp, d, pc, ev[kk], ed[kk], s[kk].x, s[kk].y, __uint_as_float(s[kk].z), now);
                     ++n_cand; n_gated += r & 1u; n_fired += r >> 1;
                 }
