@@ -338,6 +338,9 @@ static cudaError_t launch_parallel_u(const KParams& kp, const DevPtrs& d, int sm
     const u64 tiles = (kp.count + 256ull * U - 1) / (256ull * U);   // 8 warps x 32*U events
     u64 grid = (u64)sm_count * per_sm;                 // persistent: a whole number of waves
     if (grid > tiles) grid = tiles;
+    // Unordered execution only approximates event order at the granularity of what is in flight; keep
+    // that window below 1/16 of the pass so small passes stay close to the ordered semantics.
+    if (grid > tiles / 16 + 1) grid = tiles / 16 + 1;
     if (grid == 0) return cudaSuccess;
     k_traverse_parallel<SAMPLER, VISITS, U><<<(unsigned)grid, 256, 0, st>>>(kp, d);
     return cudaGetLastError();
@@ -367,6 +370,7 @@ static cudaError_t launch_block_t(const KParams& kp, const DevPtrs& d, int sm_co
     const u64 chunks = (kp.count + (32ull << LOGB) - 1) / (32ull << LOGB);
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + 7) / 8) grid = (chunks + 7) / 8;
+    if (grid > chunks / (8 * 16) + 1) grid = chunks / (8 * 16) + 1;      // in-flight window <= 1/16 of the pass (see above)
     if (grid == 0) return cudaSuccess;
     k_traverse_block<LOGB, VISITS><<<(unsigned)grid, 256, 0, st>>>(kp, d);
     return cudaGetLastError();
