@@ -84,6 +84,9 @@ struct abnn_handle {
     u64* d_total = nullptr;               // [0]: compaction total, [1..]: misc
     u64* d_counts = nullptr;              // world_size u64 (record counts exchange)
     ncclComm_t comm = nullptr;
+    // EXACT execution scratch (allocated on first use)
+    u64* d_xkeys = nullptr; u64* d_xvals = nullptr; u32* d_xcount = nullptr; void* d_xtmp = nullptr;
+    u64 x_cap = 0; size_t x_tmp_bytes = 0;
     bool timing = false;
 };
 
@@ -231,6 +234,32 @@ int append_chunk(abnn_handle* h, const abnn_synapse* host, u64 n)
     return 0;
 }
 
+// EXACT execution: phase 1 (candidates) -> radix sort by (dst, event) -> phase 3 (per-destination chains).
+int run_exact(abnn_handle* h, const KParams& kp)
+{
+    if (kp.count >= (1ull << 32)) return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution: at most 2^32-1 events per rank per pass");
+    if (kp.count > h->x_cap) {
+        cudaFree(h->d_xkeys); cudaFree(h->d_xvals); cudaFree(h->d_xtmp);
+        h->d_xkeys = h->d_xvals = nullptr; h->d_xtmp = nullptr; h->x_cap = 0;
+        const u64 cap = kp.count;
+        CU(cudaMalloc(&h->d_xkeys, 2 * cap * sizeof(u64)));
+        CU(cudaMalloc(&h->d_xvals, 2 * cap * sizeof(u64)));
+        h->x_tmp_bytes = exact_sort_temp_bytes(cap);
+        CU(cudaMalloc(&h->d_xtmp, h->x_tmp_bytes ? h->x_tmp_bytes : 16));
+        if (!h->d_xcount) CU(cudaMalloc(&h->d_xcount, sizeof(u32)));
+        h->x_cap = cap;
+    }
+    if (!kp.count) return 0;
+    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, h->d_xvals, h->d_xcount, h->sm_count, h->st));
+    u32 n = 0;
+    CU(cudaMemcpyAsync(&n, h->d_xcount, sizeof(u32), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));                 // the sort needs the item count on the host
+    int nb = 1; while ((1ull << nb) < h->N) ++nb;     // bits of a neuron id
+    CU(launch_exact_sort(h->d_xkeys, h->d_xvals, h->x_cap, n, 32 + nb, h->d_xtmp, h->x_tmp_bytes, h->st));
+    CU(launch_exact_phase3(kp, h->d, h->d_xkeys + h->x_cap, h->d_xvals + h->x_cap, h->d_xcount, n, h->sm_count, h->st));
+    return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -316,6 +345,8 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
         return fail(ABNN_ERR_UNSUPPORTED, "METAL_TID0 r-bar needs SERIAL execution");
     if (p.exec_mode == ABNN_EXEC_EXACT && p.src_view != ABNN_SRC_SNAPSHOT)
         return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution needs the SNAPSHOT src view");
+    if (p.exec_mode == ABNN_EXEC_EXACT && p.max_spikes_per_pass != 0)
+        return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution does not support the ordered spike budget (max_spikes_per_pass must be 0)");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -445,6 +476,7 @@ void abnn_destroy(abnn_handle* h)
     cudaFree(h->rs.rate); cudaFree(h->rs.iir); cudaFree(h->rs.fir); cudaFree(h->rs.smooth); cudaFree(h->rs.spikes);
     cudaFree(h->d_stats); cudaFreeHost(h->h_pin); cudaFree(h->d_scratch); cudaFree(h->d_stage);
     cudaFree(h->d_total); cudaFree(h->d_counts);
+    cudaFree(h->d_xkeys); cudaFree(h->d_xvals); cudaFree(h->d_xcount); cudaFree(h->d_xtmp);
     for (int i = 0; i < RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -667,7 +699,7 @@ int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
     switch (h->p.exec_mode) {
         case ABNN_EXEC_SERIAL:   CU(launch_traverse_serial(kp, h->d, h->st)); break;
         case ABNN_EXEC_PARALLEL: CU(launch_traverse_parallel(kp, h->d, h->sm_count, h->st)); break;
-        default: return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution is not implemented in this build");
+        default: RET(run_exact(h, kp)); break;
     }
     if (stats) CU(cudaEventRecord(h->evk, h->st));
     CU(launch_end_pass(kp, h->d.sc, h->d_stats, h->st));

@@ -9,6 +9,13 @@ cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm
 cudaError_t launch_traverse_serial(const KParams& kp, const DevPtrs& d, cudaStream_t st);
 cudaError_t launch_end_pass(const KParams& kp, DevScalars* sc, abnn_pass_stats* out, cudaStream_t st);
 
+// exact.cu — EXACT execution (two-phase, bit-identical to SERIAL)
+size_t exact_sort_temp_bytes(u64 cap);
+cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, u64* vals, u32* counter, int sm_count, cudaStream_t st);
+cudaError_t launch_exact_sort(u64* keys, u64* vals, u64 cap, u32 n, int key_bits, void* tmp, size_t tmp_bytes, cudaStream_t st);
+cudaError_t launch_exact_phase3(const KParams& kp, const DevPtrs& d, const u64* keys_sorted, const u64* vals_sorted,
+                                const u32* counter, u32 n_host, int sm_count, cudaStream_t st);
+
 // io_kernels.cu
 struct ReadoutParams {
     u32 n_input, n_output;

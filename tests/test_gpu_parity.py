@@ -152,6 +152,59 @@ def test_parallel_block_sampler_visits_exact_and_counts_close(block):
         assert np.array_equal(b.timestamps()[1], o.timestamps()[1]), f"lastVisited differs at pass {p}"
 
 
+# ---- EXACT execution: parallel and bit-identical to the serial order -----------------------------------
+@pytest.mark.parametrize("block,clock_mode", [(1, capi.CLOCK_PER_EVENT), (8, capi.CLOCK_PER_EVENT), (8, capi.CLOCK_PER_PASS)])
+def test_exact_mode_bit_exact_toy_full_size(block, clock_mode):
+    """configs[0] at FULL size (256/256/10k neurons, 1M synapses, 1M-event passes, reference graph, sine
+    input, teacher forcing, reward, growth + pruning): conflict-free parallel execution must reproduce
+    the serial oracle bit for bit — fire decisions, both timestamp arrays, weights, append order."""
+    per_pass = clock_mode == capi.CLOCK_PER_PASS
+    over = dict(TOY, exec_mode=capi.EXEC_EXACT, sample_block=block, clock_mode=clock_mode, seed=42,
+                window_pre=5 if per_pass else 2_000_000, refractory=2 if per_pass else 100_000,
+                p_new=0.02, w_prune=0.03, syn_capacity=1_050_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.build_random_graph(1); o.init_graph(capi.GRAPH_REFERENCE, 1)
+    stim = FunctionalDataset()
+    even = False
+    fired = 0
+    for p in range(5):
+        vin, exp = stim.nextInput(), stim.nextExpected()
+        for x in (b, o):
+            x.inject_inputs(vin, 1000.0); x.teacher_force(exp, 1.0 if even else 0.0)
+        even = not even
+        sb, so = b.run_pass(1_000_000), o.run_pass(1_000_000)
+        assert_same_stats(sb, so, f"pass {p}")
+        fired += so.fired
+        assert b.readout_filtered(exp).tobytes() == o.readout_filtered(exp).tobytes()
+        if p == 2:
+            ssb, sso = b.prune_and_grow(), o.prune_and_grow()
+            assert (ssb.pruned, ssb.appended, ssb.n_after) == (sso.pruned, sso.appended, sso.n_after)
+            assert sso.appended > 0
+            b.set_reward(0.02); o.set_reward(0.02)
+    assert fired > 1000
+    assert_same_state(b, o, "after 5 passes")
+
+
+def test_exact_mode_er_graph_many_conflicts():
+    """Small neuron count, many events per destination per pass (long per-destination chains)."""
+    over = dict(n_input=32, n_output=32, n_hidden=2000, n_syn=300_000, exec_mode=capi.EXEC_EXACT, sample_block=8,
+                window_pre=5_000_000, refractory=3_000, p_new=0.01, syn_capacity=400_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.init_graph(capi.GRAPH_ER_BETA, 3); o.init_graph(capi.GRAPH_ER_BETA, 3)
+    rng = np.random.default_rng(1)
+    pre = rng.integers(1, 100_000, 2064).astype(np.uint64)
+    for x in (b, o):
+        x.upload_timestamps(pre, None); x.clock = 100_000; x.set_reward(-0.5)
+    for p in range(3):
+        sb, so = b.run_pass(500_000), o.run_pass(500_000)
+        assert_same_stats(sb, so, f"pass {p}")
+        assert so.gated > 100_000 and so.fired > 1000
+    assert_same_state(b, o)
+    sb, so = b.prune_and_grow(), o.prune_and_grow()
+    assert (sb.appended, sb.n_after) == (so.appended, so.n_after) and so.appended > 10
+    assert_same_state(b, o, "after growth")
+
+
 # ---- PARALLEL execution ------------------------------------------------------------------------------
 def test_parallel_conflict_free_is_bit_exact():
     """When no two events of a pass share a destination, PARALLEL == SERIAL order bit for bit:
