@@ -23,6 +23,7 @@ EXEC_SERIAL, EXEC_EXACT, EXEC_PARALLEL = 0, 1, 2
 SRC_LIVE, SRC_SNAPSHOT = 0, 1
 RBAR_PASS_STEP, RBAR_METAL_TID0 = 0, 1
 GRAPH_REFERENCE, GRAPH_ER_BETA = 0, 1
+TABLE_AS_GIVEN, TABLE_DST_SORTED = 0, 1
 PROFILE_METAL_PARITY, PROFILE_NORTH_STAR = 0, 1
 
 
@@ -52,7 +53,7 @@ class Params(C.Structure):
         ("filter_tau", C.c_double), ("dt_sec", C.c_double), ("loss0", C.c_double),
         ("device", C.c_int32), ("rank", C.c_uint32), ("world_size", C.c_uint32),
         ("l2_persist", C.c_uint32),
-        ("sample_block", C.c_uint32), ("reserved_", C.c_uint32 * 3),
+        ("sample_block", C.c_uint32), ("table_order", C.c_uint32), ("reserved_", C.c_uint32 * 2),
     ]
 
     def copy(self) -> "Params":

@@ -234,6 +234,28 @@ int append_chunk(abnn_handle* h, const abnn_synapse* host, u64 n)
     return 0;
 }
 
+// ABNN_TABLE_DST_SORTED: keep the rank's table stably sorted by destination neuron (include/abnn.h).
+// Scratch (a second table + two key arrays) is allocated for the duration of the sort only.
+int sort_table(abnn_handle* h)
+{
+    if (h->p.table_order != ABNN_TABLE_DST_SORTED || h->n_local < 2) return 0;
+    const u64 n = h->n_local;
+    abnn_synapse* alt = nullptr; u32* keys = nullptr; void* tmp = nullptr;
+    const size_t tmp_bytes = sort_by_dst_temp_bytes(n);
+    auto release = [&] { cudaFree(alt); cudaFree(keys); cudaFree(tmp); };
+    cudaError_t e = cudaMalloc(&alt, n * sizeof(abnn_synapse));
+    if (e == cudaSuccess) e = cudaMalloc(&keys, 2 * n * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    bool in_alt = false;
+    int nb = 1; while ((1ull << nb) < h->N) ++nb;
+    if (e == cudaSuccess) e = launch_sort_by_dst(h->d_syn, alt, keys, keys + n, n, nb, tmp, tmp_bytes, &in_alt, h->st);
+    if (e == cudaSuccess && in_alt) e = cudaMemcpyAsync(h->d_syn, alt, n * sizeof(abnn_synapse), cudaMemcpyDeviceToDevice, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    release();
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ABNN_ERR_CUDA, std::string("sort_table: ") + cudaGetErrorString(e)); }
+    return 0;
+}
+
 // EXACT execution: phase 1 (candidates) -> radix sort by (dst, event) -> phase 3 (per-destination chains).
 int run_exact(abnn_handle* h, const KParams& kp)
 {
@@ -334,6 +356,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (!p.world_size || p.rank >= p.world_size) return fail(ABNN_ERR_INVALID, "bad rank/world_size");
     if (p.sampler > 1 || p.release_rng > 1 || p.clock_mode > 1 || p.exec_mode > 2 || p.src_view > 1 || p.rbar_mode > 1)
         return fail(ABNN_ERR_INVALID, "unknown mode value");
+    if (p.table_order > ABNN_TABLE_DST_SORTED) return fail(ABNN_ERR_INVALID, "unknown table_order");
     if (p.sample_block > 32 || (p.sample_block & (p.sample_block - 1)))
         return fail(ABNN_ERR_INVALID, "sample_block must be a power of two <= 32 (0 = 1)");
     if (!p.n_output || p.fir_size == 0 || p.fir_size > ABNN_MAX_FIR) return fail(ABNN_ERR_INVALID, "bad n_output / fir_size");
@@ -532,6 +555,7 @@ int abnn_upload_synapses(abnn_handle* h, const abnn_synapse* syn, uint64_t n)
     if (!syn && n) return fail(ABNN_ERR_INVALID, "null table");
     h->n_local = 0;
     RET(append_chunk(h, syn, n));
+    RET(sort_table(h));
     h->counts_dirty = true;
     if (h->p.world_size == 1) h->n_local_all.assign(1, h->n_local);
     return 0;
@@ -559,6 +583,7 @@ int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed)
         if (h->hi == h->lo && g1 > g0) return fail(ABNN_ERR_INVALID, "rank owns no neurons");
         CU(launch_init_er_beta(h->d_syn, g0, g1 - g0, seed, h->N, h->lo, h->hi, h->sm_count, h->st));
         h->n_local = g1 - g0;
+        RET(sort_table(h));
         for (u32 k = 0; k < p.world_size; ++k)
             h->n_local_all[k] = (u64)((unsigned __int128)p.n_syn * (k + 1) / p.world_size) -
                                 (u64)((unsigned __int128)p.n_syn * k / p.world_size);
@@ -593,6 +618,7 @@ int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed)
             ++idx;
             if (fill == chunk || idx == p.n_syn) { RET(append_chunk(h, buf.data(), fill)); fill = 0; }
         }
+        RET(sort_table(h));
         h->counts_dirty = true;
         if (p.world_size == 1) h->n_local_all.assign(1, h->n_local);
         return 0;
@@ -647,6 +673,7 @@ int abnn_load_bnn(abnn_handle* h, const char* path)
     }
     std::fclose(f);
     h->n_local = n; h->n_local_all.assign(1, n); h->counts_dirty = false;
+    RET(sort_table(h));
     return 0;
 }
 
@@ -859,6 +886,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
             CU(launch_grow_append(list, m, h->d_syn, h->n_local, h->p.w_init, h->st));
             h->n_local += m;
             s.appended = m; s.dropped = owned - m;
+            if (m) RET(sort_table(h));
         }
         k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
         CU(cudaGetLastError());

@@ -50,6 +50,12 @@ cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cu
 cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 n_pow2, u32 dst_lo, u32 dst_hi, u32* d_owned, cudaStream_t st);
 cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st);
 
+// Stable sort of n records by dst (ABNN_TABLE_DST_SORTED). alt/keys/keys_alt: n-element scratch buffers.
+// The sorted table ends up in `alt` when *result_in_alt (the caller copies it back), else in `syn`.
+size_t sort_by_dst_temp_bytes(u64 n);
+cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, u32* keys_alt, u64 n, int key_bits,
+                               void* tmp, size_t tmp_bytes, bool* result_in_alt, cudaStream_t st);
+
 // init.cu
 cudaError_t launch_init_er_beta(abnn_synapse* syn, u64 g0, u64 count, u64 seed, u64 n_neuron, u64 dlo, u64 dhi,
                                 int sm_count, cudaStream_t st);

@@ -9,6 +9,8 @@
 //                      abnn_upload_synapses.
 //   * k_grow_*       : growth candidates staged by firing events are ordered by the tick ordinal of
 //                      the event that produced them (bitonic sort) and appended in that order.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -119,6 +121,38 @@ cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cu
     u32* ticket = reinterpret_cast<u32*>(scratch);
     u64* desc = reinterpret_cast<u64*>(reinterpret_cast<char*>(scratch) + 16);
     k_compact<<<(unsigned)tiles, CT, 0, st>>>(a, ticket, desc, d_total);
+    return cudaGetLastError();
+}
+
+// ---- ABNN_TABLE_DST_SORTED: stable sort of the table by destination neuron -------------------------
+// LSD radix sort (cub) on key = dst with the 16-byte record as the value: stable, so records that
+// share a destination keep their table order. One-off cost at graph load / after a growth step:
+// 2 x ceil(bits/8) streaming passes over the table.
+__global__ void k_extract_dst(const abnn_synapse* syn, u64 n, u32* keys)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) keys[i] = syn[i].dst;
+}
+size_t sort_by_dst_temp_bytes(u64 n)
+{
+    size_t b = 0;
+    cub::DoubleBuffer<u32> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint4> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, b, k, v, (long long)n, 0, 32);
+    return b;
+}
+cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, u32* keys_alt, u64 n, int key_bits,
+                               void* tmp, size_t tmp_bytes, bool* result_in_alt, cudaStream_t st)
+{
+    *result_in_alt = false;
+    if (n < 2) return cudaSuccess;
+    u64 blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_extract_dst<<<(unsigned)blocks, 256, 0, st>>>(syn, n, keys);
+    cub::DoubleBuffer<u32> k(keys, keys_alt);
+    cub::DoubleBuffer<uint4> v(reinterpret_cast<uint4*>(syn), reinterpret_cast<uint4*>(alt));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, key_bits, st);
+    if (e != cudaSuccess) return e;
+    *result_in_alt = v.Current() != reinterpret_cast<uint4*>(syn);
     return cudaGetLastError();
 }
 

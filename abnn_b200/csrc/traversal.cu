@@ -5,11 +5,16 @@
 // (README.md:77), uint64 timestamps with a per-event clock (README.md:62-63,85), lastVisited writes
 // (README.md:84), and the per-event arithmetic of brain.metal:70-126 unchanged.
 //
-//   k_traverse_parallel : the throughput kernel. HBM-bound random 16-byte gathers of SynapsePacked,
-//                         one L2 read of lastFired[src] and one L2 RED.MAX on lastVisited[dst] per
-//                         event; everything past the pre-spike window gate is a rare path where
-//                         same-dst lanes of a warp are serialised with match.any and timestamps
-//                         move with 64-bit atomicMax.
+//   k_traverse_line     : the throughput kernel (PHILOX sampler, sample_block = 8): every warp streams
+//                         Philox-chosen 128-byte lines of the synapse table into its own shared-memory
+//                         ring with cp.async.bulk (TMA bulk copies completing on mbarriers), so HBM
+//                         latency is hidden by the ring depth, not by registers or occupancy; per event
+//                         one L2 read of lastFired[src]; lastVisited[dst] moves with one RED.MAX.64 per
+//                         run of equal destinations (one per line when the table is dst-sorted); events
+//                         that pass the pre-spike window are resolved per destination, in event order,
+//                         inside the warp (match.any + ballot chain) and publish with 64-bit atomicMax.
+//   k_traverse_parallel : iid PHILOX sampler (16-byte random gathers) and the SWEEP sampler.
+//   k_traverse_block    : sample_block = 2, 4, 16, 32 (register-staged).
 //   k_traverse_serial   : one thread walks the events in index order (the bit-exact order of the
 //                         oracle). Reference for the EXACT mode and the parity tests.
 //   k_end_pass          : r-bar step, clock advance, counters -> stats slot (no host round trip).
@@ -171,6 +176,72 @@ __device__ __forceinline__ u32 gated_path(const KParams& kp, const DevPtrs& d, c
     return result;
 }
 
+// Gated path without the spike budget (north-star profile). Called by the whole (converged) warp.
+// Candidates of the warp that share a destination form a chain that must run in event (= lane)
+// order, because a fire moves lastFired[dst] for the events behind it. The chain state is one
+// register (ld): every candidate evaluates against the value in memory; the first candidate of a
+// destination that fires is final together with everything before it, the candidates behind it
+// re-evaluate against its timestamp — one round per fire in a chain, zero extra rounds when nothing
+// fires (the common case), and no memory round trip between chain members. Exactly the serial
+// order for the events of one warp; across warps lastFired moves with atomicMax.
+// Returns bit0 = gated (weight written), bit1 = fired.
+__device__ __forceinline__ u32 chain_path(const KParams& kp, const DevPtrs& d, const PassConsts& pc, bool cand, u64 i,
+                                          u64 edge, u32 src, u32 dst, float w, u64 now)
+{
+    const unsigned cmask = __ballot_sync(0xffffffffu, cand);
+    if (!cand) return 0;
+    const unsigned lane  = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(cmask, dst);
+    u64 ld = __ldcg(d.live + dst);                                                          // brain.metal:79
+    const u64 eid = pc.event_base + i;
+    Philox4 r{0, 0, 0, 0};
+    if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_philox(kp, eid);
+    const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
+    const bool rel = release_test(kp, w, u);                                                // brain.metal:91-92
+    bool settled = false, skip = true, fired = false;
+    u64 gap = 0;
+    do {
+        if (!settled) {
+            gap = ld <= now ? now - ld : ld - now;       // symmetric: a later event of another warp may have fired already
+            skip = gap <= kp.refractory;                                                    // brain.metal:79-83
+            fired = !skip && rel;
+        }
+        const unsigned F = __ballot_sync(cmask, fired && !settled) & peers;   // unsettled peers that fire under the current ld
+        const int first = F ? __ffs(F) - 1 : (int)lane;
+        const u64 now_first = __shfl_sync(cmask, now, first);
+        if (!settled) {
+            if (F == 0 || lane <= (unsigned)first) settled = true;           // nothing before me fires: my decision stands
+            else if (now_first > ld) ld = now_first;                          // brain.metal:125-126 seen by the events behind it
+        }
+    } while (__any_sync(cmask, !settled));
+    if (skip) return 0;
+    __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, gap));                   // brain.metal:122
+    if (!fired) return 1;
+    atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
+    stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.w);
+    return 3;
+}
+
+// Events that passed the pre-spike window: budgeted runs keep the turn-based path (the global spike
+// budget is claimed per fire), everything else resolves its chains in registers.
+__device__ __forceinline__ u32 resolve_candidates(const KParams& kp, const DevPtrs& d, const PassConsts& pc, bool cand, u64 i,
+                                                  u64 edge, u32 src, u32 dst, float w, u64 now)
+{
+    if (!__any_sync(0xffffffffu, cand)) return 0;
+    if (!kp.budget_on) return chain_path(kp, d, pc, cand, i, edge, src, dst, w, now);
+    return cand ? gated_path(kp, d, pc, i, edge, src, dst, w, now) : 0u;
+}
+
+// lastVisited[dst] = max(., now) (README.md:84) once per run of equal destinations in adjacent lanes:
+// `now` grows with the lane, so the last lane of a run carries the run's maximum. With a dst-sorted
+// table a 128-byte line is one run -> one RED.MAX.64 per line instead of eight. Whole warp calls.
+__device__ __forceinline__ void visit(const DevPtrs& d, bool ok, u32 dst, u64 now)
+{
+    const u32 key = ok ? dst : 0xFFFFFFFFu;
+    const u32 next = __shfl_down_sync(0xffffffffu, key, 1);
+    if (ok && ((threadIdx.x & 31) == 31 || next != key)) atomicMax(d.visited + dst, now);   // RED.MAX.64 at L2
+}
+
 __device__ __forceinline__ void flush_counters(const DevPtrs& d, u32 n_cand, u32 n_gated, u32 n_fired, u32* s_cnt)
 {
     n_cand = __reduce_add_sync(0xffffffffu, n_cand);
@@ -214,7 +285,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
     const u64 tile = 256ull * U;
     for (u64 base = (u64)blockIdx.x * tile; base < kp.count; base += (u64)gridDim.x * tile) {
         u64   edge[U];
-        uint4 s[U];
+        uint4 s[U] = {};
         u64   lp[U];
         bool  ok[U];
 #pragma unroll
@@ -237,14 +308,12 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
             if (ok[j]) lp[j] = __ldcg(d.view + s[j].x);                          // brain.metal:73
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            if (!ok[j]) continue;
             const u64 i = base + (u64)j * 256 + threadIdx.x;
             const u64 now = event_now(kp, pc.clock, i);
-            if (VISITS) atomicMax(d.visited + s[j].y, now);                      // README.md:84 (RED.MAX.64 at L2)
-            if (now - lp[j] <= kp.window_pre || (!kp.snapshot && lp[j] > now)) { // brain.metal:74 (live view: a later spike is recent)
-                const u32 r = gated_path(kp, d, pc, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
-                ++n_cand; n_gated += r & 1u; n_fired += r >> 1;
-            }
+            if (VISITS) visit(d, ok[j], s[j].y, now);                            // README.md:84
+            const bool cand = ok[j] && (now - lp[j] <= kp.window_pre || (!kp.snapshot && lp[j] > now));   // brain.metal:74 (live view: a later spike is recent)
+            const u32 r = resolve_candidates(kp, d, pc, cand, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
+            n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
         }
     }
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
@@ -282,7 +351,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
 #pragma unroll
         for (int k0 = 0; k0 < B; k0 += KB) {
             u64   ev[KB], ed[KB], lp[KB];
-            uint4 s[KB];
+            uint4 s[KB] = {};
             bool  ok[KB];
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk) {
@@ -298,15 +367,146 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
                 if (ok[kk]) lp[kk] = __ldcg(d.view + s[kk].x);
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk) {
-                if (!ok[kk]) continue;
                 const u64 now = event_now(kp, pc.clock, ev[kk]);
-                if (VISITS) atomicMax(d.visited + s[kk].y, now);
-                if (now - lp[kk] <= kp.window_pre || (!kp.snapshot && lp[kk] > now)) {
-                    const u32 r = gated_path(kp, d, pc, ev[kk], ed[kk], s[kk].x, s[kk].y, __uint_as_float(s[kk].z), now);
-                    ++n_cand; n_gated += r & 1u; n_fired += r >> 1;
-                }
+                if (VISITS) visit(d, ok[kk], s[kk].y, now);
+                const bool cand = ok[kk] && (now - lp[kk] <= kp.window_pre || (!kp.snapshot && lp[kk] > now));
+                const u32 r = resolve_candidates(kp, d, pc, cand, ev[kk], ed[kk], s[kk].x, s[kk].y, __uint_as_float(s[kk].z), now);
+                n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
             }
         }
+    }
+    flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
+}
+
+
+// ================================================================================================
+// Line sampler (sample_block = 8): one Philox draw = one 128-byte line of the table = 8 events.
+//
+// Each warp owns a ring of LINE_STAGES shared-memory stages. A stage holds one chunk = 32 lines = 256
+// events: lane L draws the line of group L and issues ONE cp.async.bulk (TMA bulk copy, UBLKCP) of that
+// line into the stage; the 32 copies of a chunk complete on the stage's mbarrier (expect_tx = bytes).
+// The warp refills a stage right after it consumed it, so LINE_STAGES-1 chunks (12 KB per warp) are
+// always in flight behind the one being processed: HBM latency is covered by the ring, not by
+// registers. The copies carry an L2 evict_first policy — the table is a stream and must not displace
+// the timestamp arrays that the access-policy window keeps resident.
+// Consumption: in step k lane l handles record (l & 7) of group 4k + (l >> 3), i.e. the warp reads 512
+// contiguous bytes of the stage (conflict-free LDS.128). The eight lastFired[src] reads of a lane are
+// issued back to back before any of them is used.
+constexpr int LINE_STAGES = 3;
+constexpr int LINE_STAGE_BYTES = 32 * 128;
+constexpr int LINE_WARPS = 8;
+constexpr size_t LINE_SMEM = (size_t)LINE_WARPS * LINE_STAGES * (LINE_STAGE_BYTES + 32 * sizeof(u64) + sizeof(u64));
+
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+    u32 done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar, u64 policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+
+template <int VISITS>
+__global__ void __launch_bounds__(256, 2) k_traverse_line(const __grid_constant__ KParams kp, const DevPtrs d)
+{
+    constexpr int LOGB = 3, B = 8;
+    extern __shared__ __align__(128) unsigned char line_smem[];
+    __shared__ u32 s_cnt[3];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* ring = line_smem + (size_t)warp * LINE_STAGES * LINE_STAGE_BYTES;
+    u64* meta = reinterpret_cast<u64*>(line_smem + (size_t)LINE_WARPS * LINE_STAGES * LINE_STAGE_BYTES) + warp * LINE_STAGES * 32;
+    u64* bars = reinterpret_cast<u64*>(line_smem + (size_t)LINE_WARPS * LINE_STAGES * (LINE_STAGE_BYTES + 32 * sizeof(u64))) + warp * LINE_STAGES;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LINE_STAGES; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    u64 policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const PassConsts pc{d.sc->clock, d.sc->event_base, d.sc->tick_base, d.sc->reward, d.sc->rbar};
+    u32 n_cand = 0, n_gated = 0, n_fired = 0;
+    const u32 rec = lane & (B - 1);
+    const u64 warps_total = (u64)gridDim.x * LINE_WARPS, warp_global = (u64)blockIdx.x * LINE_WARPS + warp;
+    const u64 n_chunks = (kp.count + 32ull * B - 1) / (32ull * B);
+
+    // lane L draws the line of group L of chunk c and starts its copy into stage s
+    auto issue = [&](u64 c, int s) {
+        const u64 i0 = (c * 32 + lane) << LOGB;
+        u64 be = ~0ull;
+        u32 bytes = 0;
+        if (i0 < kp.count) {
+            const Philox4 r = event_philox(kp, pc.event_base + i0);
+            be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGB;
+            const u64 left = kp.n_local - be;                         // the table's last line may be short
+            bytes = (u32)(left < B ? left : B) * (u32)sizeof(abnn_synapse);
+        }
+        meta[s * 32 + lane] = be;
+        const u32 total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_expect_tx(bars + s, total);
+        __syncwarp();
+        if (bytes) bulk_load(ring + (size_t)s * LINE_STAGE_BYTES + lane * 128, d.syn + be, bytes, bars + s, policy);
+    };
+
+    u64 c_next = warp_global;
+#pragma unroll
+    for (int s = 0; s < LINE_STAGES; ++s) {
+        if (c_next < n_chunks) issue(c_next, s);
+        c_next += warps_total;
+    }
+    u32 phases = 0;
+    int s = 0;
+    for (u64 c = warp_global; c < n_chunks; c += warps_total) {
+        mbar_wait(bars + s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+        const unsigned char* stage = ring + (size_t)s * LINE_STAGE_BYTES + lane * 16;
+        const u64* mb = meta + s * 32 + (lane >> LOGB);
+        u64 lp[B];
+        u32 okm = 0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {                                  // 8 lastFired[src] reads in flight per lane
+            const u64 be = mb[k * 4];
+            const u64 ev = ((c * 32 + k * 4 + (lane >> LOGB)) << LOGB) + rec;
+            const bool ok = be != ~0ull && ev < kp.count && be + rec < kp.n_local;
+            lp[k] = 0;
+            if (ok) {
+                okm |= 1u << k;
+                lp[k] = __ldcg(d.view + *reinterpret_cast<const u32*>(stage + k * 512));   // brain.metal:73
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const bool ok = (okm >> k) & 1u;
+            const uint4 sy = *reinterpret_cast<const uint4*>(stage + k * 512);             // brain.metal:70
+            const u64 ev = ((c * 32 + k * 4 + (lane >> LOGB)) << LOGB) + rec;
+            const u64 now = event_now(kp, pc.clock, ev);
+            if (VISITS) visit(d, ok, sy.y, now);                                            // README.md:84
+            const bool cand = ok && (now - lp[k] <= kp.window_pre || (!kp.snapshot && lp[k] > now));   // brain.metal:74
+            const u32 r = resolve_candidates(kp, d, pc, cand, ev, mb[k * 4] + rec, sy.x, sy.y, __uint_as_float(sy.z), now);
+            n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
+        }
+        __syncwarp();                                                   // every lane is done reading the stage
+        if (c_next < n_chunks) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c_next, s);
+        }
+        c_next += warps_total;
+        s = s + 1 == LINE_STAGES ? 0 : s + 1;
     }
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
 }
@@ -359,6 +559,30 @@ static cudaError_t launch_parallel_t(const KParams& kp, const DevPtrs& d, int sm
     }
 }
 
+
+template <int VISITS>
+static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
+{
+    static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_traverse_line<VISITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (!kp.count || !kp.n_local) return cudaSuccess;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line<VISITS>, 256, LINE_SMEM);
+    if (per_sm < 1) per_sm = 1;
+    if (bps > 0 && bps < per_sm) per_sm = bps;
+    const u64 chunks = (kp.count + 255) / 256;
+    u64 grid = (u64)sm_count * per_sm;
+    if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
+    if (grid > chunks / (LINE_WARPS * 16) + 1) grid = chunks / (LINE_WARPS * 16) + 1;   // in-flight window <= 1/16 of the pass
+    k_traverse_line<VISITS><<<(unsigned)grid, 256, LINE_SMEM, st>>>(kp, d);
+    return cudaGetLastError();
+}
+
 template <int LOGB, int VISITS>
 static cudaError_t launch_block_t(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
@@ -390,6 +614,8 @@ static cudaError_t launch_block(const KParams& kp, const DevPtrs& d, int sm_coun
 cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     const bool ph = kp.sampler == ABNN_SAMPLER_PHILOX, vis = kp.track_visits != 0;
+    static const bool legacy_block = getenv("ABNN_TRAV_LEGACY_BLOCK") != nullptr;      // A/B measurements only
+    if (ph && kp.sample_block == 8 && !legacy_block) return vis ? launch_line<1>(kp, d, sm_count, st) : launch_line<0>(kp, d, sm_count, st);
     if (ph && kp.sample_block > 1) return vis ? launch_block<1>(kp, d, sm_count, st) : launch_block<0>(kp, d, sm_count, st);
     if (ph && vis)  return launch_parallel_t<ABNN_SAMPLER_PHILOX, 1>(kp, d, sm_count, st);
     if (ph && !vis) return launch_parallel_t<ABNN_SAMPLER_PHILOX, 0>(kp, d, sm_count, st);

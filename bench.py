@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--events", type=int, default=150_000_000)
     ap.add_argument("--sampler", default="philox", choices=["philox", "sweep"])
     ap.add_argument("--block", type=int, default=8, help="PHILOX sampler granularity in records (8 = one 128-byte HBM line per draw; 1 = iid)")
+    ap.add_argument("--table-order", default="dst", choices=["dst", "given"],
+                    help="dst = ABNN_TABLE_DST_SORTED (stable sort by destination neuron at load), given = generation order")
     ap.add_argument("--warm-frac", type=float, default=0.25,
                     help="fraction of neurons whose lastFired is pre-seeded inside the pre-spike window (SURVEY §8d 'warm' variant)")
     ap.add_argument("--src-view", default="snapshot", choices=["snapshot", "live"])
@@ -132,6 +134,7 @@ def base_params(args, O, capi, rank, world, events):
                 exec_mode=capi.EXEC_PARALLEL, window_pre=5 * events, refractory=2 * events,
                 track_visits=0 if args.no_visits else 1, l2_persist=0 if args.no_l2_persist else 1,
                 rank=rank, world_size=world, device=-1, sample_block=args.block,
+                table_order=capi.TABLE_DST_SORTED if args.table_order == "dst" else capi.TABLE_AS_GIVEN,
                 src_view=capi.SRC_SNAPSHOT if args.src_view == "snapshot" else capi.SRC_LIVE)
     return O.default_params(capi.PROFILE_NORTH_STAR, **over)
 
@@ -310,7 +313,7 @@ def main():
             "metric": "synaptic events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64 timestamps + f32 weights", "data": "synthetic",
-            "config": {"workload": workload, "sampler": args.sampler, "sample_block": args.block, "exec_mode": "parallel", "clock": "per_event",
+            "config": {"workload": workload, "sampler": args.sampler, "sample_block": args.block, "table_order": args.table_order, "exec_mode": "parallel", "clock": "per_event",
                        "graph": "ER endpoints, Beta(2,8) weights (Philox)", "window_pre_passes": 5, "refractory_passes": 2,
                        "warm_fraction": args.warm_frac, "track_visits": not args.no_visits,
                        "parallelism": f"dst-shard x{world}" if world > 1 else "single GPU",

@@ -79,6 +79,14 @@ enum abnn_graph_kind {
                                  U[.4,.8) then hid->hid U[.1,.2)                               */
     ABNN_GRAPH_ER_BETA   = 1 /*  Erdos-Renyi endpoints, w ~ Beta(2,8) (README.md:134-135), Philox-keyed by edge */
 };
+enum abnn_table_order {     /* HBM layout of this rank's synapse table                       */
+    ABNN_TABLE_AS_GIVEN   = 0,/*  records stay in upload / generation order (brain-engine.cpp:37-52)  */
+    ABNN_TABLE_DST_SORTED = 1 /*  stable sort by dst after every upload / init / load / growth step: the
+                                 records that target one neuron are contiguous, so a 128-byte line of
+                                 the table (sample_block = 8) touches one lastFired/lastVisited sector
+                                 instead of eight. Table order is part of the semantics (edge(e) indexes
+                                 it); the oracle applies the same stable sort.                  */
+};
 enum abnn_profile {
     ABNN_PROFILE_METAL_PARITY = 0, /* SWEEP, XORSHIFT, PER_PASS, SERIAL, LIVE, METAL_TID0, budget 2560 */
     ABNN_PROFILE_NORTH_STAR   = 1  /* PHILOX, PHILOX, PER_EVENT, PARALLEL, SNAPSHOT, PASS_STEP          */
@@ -154,7 +162,8 @@ typedef struct abnn_params {
      * DRAM fetch granularity: a random 16-byte gather costs a whole line, profiles/r1_probe_gather.md).
      * Power of two, <= 32. Every edge is still sampled with equal probability. */
     uint32_t sample_block;
-    uint32_t reserved_[3];
+    uint32_t table_order;          /* abnn_table_order                                          */
+    uint32_t reserved_[2];
 } abnn_params;
 
 #define ABNN_MAX_FIR 64u

@@ -94,6 +94,21 @@ void recount(ob_handle* h)
 {
     if (h->p.world_size == 1) h->n_local_all.assign(1, h->syn.size());
 }
+
+// ABNN_TABLE_DST_SORTED (include/abnn.h): stable sort of the shard's table by dst (counting sort:
+// records with equal dst keep their relative order). No reference counterpart — a layout rule of
+// the north-star design; table order matters because edge(e) indexes the table.
+void sort_table(ob_handle* h)
+{
+    if (h->p.table_order != ABNN_TABLE_DST_SORTED || h->syn.empty()) return;
+    const uint64_t span = h->hi - h->lo;
+    std::vector<uint64_t> start(span + 1, 0);
+    for (const auto& s : h->syn) ++start[s.dst - h->lo + 1];
+    for (uint64_t d = 0; d < span; ++d) start[d + 1] += start[d];
+    std::vector<abnn_synapse> out(h->syn.size());
+    for (const auto& s : h->syn) out[start[s.dst - h->lo]++] = s;
+    h->syn.swap(out);
+}
 }  // namespace
 
 extern "C" {
@@ -162,6 +177,7 @@ int ob_upload_synapses(ob_handle* h, const abnn_synapse* s, uint64_t n)
     for (uint64_t i = 0; i < n; ++i)
         if (s[i].dst >= h->lo && s[i].dst < h->hi) h->syn.push_back(s[i]);
     if (h->syn.size() > h->cap) return ABNN_ERR_CAPACITY;
+    sort_table(h);
     recount(h);
     return 0;
 }
@@ -236,6 +252,7 @@ int ob_init_graph(ob_handle* h, uint32_t kind, uint64_t seed)
             for (uint32_t k = 0; k < p.world_size; ++k)
                 h->n_local_all[k] = uint64_t((unsigned __int128)p.n_syn * (k + 1) / p.world_size) -
                                     uint64_t((unsigned __int128)p.n_syn * k / p.world_size);
+        sort_table(h);
         recount(h);
         return 0;
     }
@@ -476,6 +493,7 @@ uint64_t ob_grow_apply(ob_handle* h, const void* cands, uint64_t n, uint64_t* dr
         ++app;
     }
     h->grow.clear();
+    if (app) sort_table(h);
     if (dropped) *dropped = drop;
     return app;
 }

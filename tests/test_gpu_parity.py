@@ -206,6 +206,78 @@ def test_exact_mode_er_graph_many_conflicts():
     assert_same_state(b, o, "after growth")
 
 
+# ---- dst-sorted table layout (ABNN_TABLE_DST_SORTED) ----------------------------------------------------
+@pytest.mark.parametrize("mode", [capi.EXEC_SERIAL, capi.EXEC_EXACT])
+def test_dst_sorted_table_bit_exact(mode):
+    """The device's stable radix sort by dst == the oracle's counting sort, after upload and after growth;
+    SERIAL and EXACT execution over the sorted table stay bit-exact."""
+    rng = np.random.default_rng(21)
+    N, n = 5000, 300_007
+    syn = random_graph(rng, n, N, 0.2, 1.0, dst_lo=16)
+    pre = rng.integers(1, 40_000, N).astype(np.uint64)
+    over = dict(n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, exec_mode=mode, sample_block=8,
+                table_order=capi.TABLE_DST_SORTED, window_pre=60_000, refractory=30_000, p_new=0.1, w_prune=0.21,
+                syn_capacity=n + 20_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(pre, None); x.clock = 40_000; x.set_reward(0.1)
+    assert b.download_synapses().tobytes() == syn[np.argsort(syn["dst"], kind="stable")].tobytes()
+    for p in range(3):
+        sb, so = b.run_pass(100_001), o.run_pass(100_001)
+        assert_same_stats(sb, so, f"pass {p}")
+        assert so.gated > 500
+        if p == 1:
+            ssb, sso = b.prune_and_grow(), o.prune_and_grow()
+            assert (ssb.pruned, ssb.appended, ssb.n_after) == (sso.pruned, sso.appended, sso.n_after)
+            assert sso.appended > 0 and sso.pruned > 0
+    assert_same_state(b, o)
+
+
+def test_line_kernel_sorted_table_single_warp_chains_exact():
+    """PARALLEL line kernel over a dst-sorted table with ONE chunk in flight per destination: 64 destinations
+    with 4096 synapses each and passes of 256 events (= one warp, one chunk). Lines of a chunk share
+    destinations, so the in-warp chain resolution (match.any + ballot) carries every same-destination
+    dependency, and the result must equal the serial oracle bit for bit."""
+    rng = np.random.default_rng(33)
+    N, n = 64, 64 * 4096
+    syn = np.zeros(n, O.SYN_DTYPE)
+    syn["src"] = rng.integers(0, N, n); syn["dst"] = np.repeat(np.arange(N), 4096)
+    syn["w"] = rng.uniform(0.3, 1.0, n).astype(np.float32)
+    over = dict(n_input=8, n_output=8, n_hidden=N - 16, n_syn=n, exec_mode=capi.EXEC_PARALLEL, sample_block=8,
+                table_order=capi.TABLE_DST_SORTED, window_pre=10**9, refractory=3)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(np.full(N, 1, np.uint64), None); x.clock = 1000; x.set_reward(0.2)
+    fired = 0
+    for p in range(40):
+        sb, so = b.run_pass(256), o.run_pass(256)
+        assert_same_stats(sb, so, f"pass {p}")
+        fired += so.fired
+    assert fired > 500
+    assert_same_state(b, o)
+
+
+def test_line_kernel_sorted_table_statistical():
+    """PARALLEL line kernel, dst-sorted ER graph at 2M synapses: lastVisited exact (order-free max, one RED per
+    run of equal destinations), gated / fired counts within 8 % + 5 sigma of the serial oracle."""
+    over = dict(n_input=64, n_output=64, n_hidden=200_000, n_syn=2_000_003, exec_mode=capi.EXEC_PARALLEL,
+                sample_block=8, table_order=capi.TABLE_DST_SORTED, window_pre=3_000_000, refractory=500_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.init_graph(capi.GRAPH_ER_BETA, 5); o.init_graph(capi.GRAPH_ER_BETA, 5)
+    assert b.download_synapses().tobytes() == o.download_synapses().tobytes()
+    rng = np.random.default_rng(9)
+    pre = rng.integers(1, 1_000_000, 200_128).astype(np.uint64)
+    for x in (b, o):
+        x.upload_timestamps(pre, None); x.clock = 1_000_000; x.set_reward(0.0)
+    for p in range(3):
+        sb, so = b.run_pass(700_001), o.run_pass(700_001)
+        assert sb.events == so.events and (p > 0 or sb.candidates == so.candidates)
+        for f in ("gated", "fired"):
+            g, w = getattr(sb, f), getattr(so, f)
+            assert abs(g - w) <= 0.08 * w + 5 * np.sqrt(w + 1), (p, f, g, w)
+        assert np.array_equal(b.timestamps()[1], o.timestamps()[1]), f"lastVisited differs at pass {p}"
+
+
 # ---- PARALLEL execution ------------------------------------------------------------------------------
 def test_parallel_conflict_free_is_bit_exact():
     """When no two events of a pass share a destination, PARALLEL == SERIAL order bit for bit:

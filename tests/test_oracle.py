@@ -192,3 +192,31 @@ def test_readout_restatement_matches_reference_filter(oracle):
             want = np.minimum(sm / maxobs, np.float32(1.0)).astype(np.float32)
             assert np.array_equal(got, want), k
     assert np.array_equal(np.array(outs).view(np.uint32), np.array(gold["readout_bits"], dtype=np.uint32))
+
+
+def test_dst_sorted_table_is_a_stable_sort(oracle):
+    """ABNN_TABLE_DST_SORTED: the oracle's table equals numpy's stable sort by dst after upload and
+    after a growth step (new records land behind the existing ones of their destination)."""
+    rng = np.random.default_rng(4)
+    n, N = 50_000, 700
+    syn = np.zeros(n, oracle.SYN_DTYPE)
+    syn["src"] = rng.integers(0, N, n); syn["dst"] = rng.integers(0, N, n)
+    syn["w"] = rng.uniform(0.3, 1.0, n).astype(np.float32)
+    p = oracle.default_params(capi.PROFILE_NORTH_STAR, n_input=8, n_output=8, n_hidden=N - 16, n_syn=n,
+                              exec_mode=capi.EXEC_SERIAL, table_order=capi.TABLE_DST_SORTED, sample_block=8,
+                              window_pre=10**9, refractory=5, p_new=0.5, syn_capacity=n + 10_000)
+    o = oracle.OracleB(p)
+    o.upload_synapses(syn)
+    want = syn[np.argsort(syn["dst"], kind="stable")]
+    assert o.download_synapses().tobytes() == want.tobytes()
+    o.upload_timestamps(np.full(N, 1, np.uint64), None); o.clock = 100
+    st = o.run_pass(40_000)
+    assert st.fired > 100 and st.grown > 50
+    before = o.download_synapses()
+    ss = o.prune_and_grow()
+    after = o.download_synapses()
+    assert ss.appended == st.grown and len(after) == n + ss.appended
+    assert np.all(np.diff(after["dst"].astype(np.int64)) >= 0)
+    # existing records keep their relative order; the new ones (w == w_init) sit at the end of their destination's run
+    old = after[after["w"] != np.float32(0.1)]
+    assert old.tobytes() == before[before["w"] != np.float32(0.1)].tobytes()
