@@ -427,7 +427,9 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     for (int i = 0; i < RING; ++i) CUH(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     CUH(cudaMalloc(&h->d_syn, h->cap * sizeof(abnn_synapse)));
     // timestamps: [view | visited | live] in one allocation so one access-policy window covers the
-    // two arrays every event touches (view read, visited RED); LIVE src view: [live | visited].
+    // arrays every event touches (view read, visited RED); LIVE src view: [live | visited].
+    // (Measured: a RED.MAX that misses L2 costs more than a read that misses — with [view | live] in
+    // the window instead, the pass is 30 % slower. profiles/r1_notes.md)
     const u64 npad = (h->npad + 31) & ~31ull;
     const bool snap = p.src_view == ABNN_SRC_SNAPSHOT;
     const u64 arrays = snap ? 3 : 2;
@@ -465,9 +467,13 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     CUH(cudaMalloc(&h->d_total, 8 * sizeof(u64)));
     CUH(cudaMalloc(&h->d_counts, p.world_size * sizeof(u64)));
 
-    // L2 residency of the timestamp arrays (north star item 2)
+    // L2 residency of the timestamp arrays (north star item 2). Tuning knobs (measurements only):
+    // ABNN_L2_ARRAYS = arrays covered by the window, ABNN_L2_MISS = 1 -> lines of the window that do not
+    // get the persisting property are "normal" instead of "streaming".
     if (p.l2_persist && max_persist > 0 && max_window > 0) {
-        const size_t hot = (size_t)2 * npad * sizeof(u64);
+        const int n_arr = getenv("ABNN_L2_ARRAYS") ? atoi(getenv("ABNN_L2_ARRAYS")) : 2;
+        const bool miss_normal = getenv("ABNN_L2_MISS") && atoi(getenv("ABNN_L2_MISS")) == 1;
+        const size_t hot = (size_t)std::min<u64>((u64)std::max(1, n_arr), arrays) * npad * sizeof(u64);
         size_t want = std::min<size_t>(hot, (size_t)max_persist);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             size_t got = 0;
@@ -476,8 +482,9 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
             attr.accessPolicyWindow.base_ptr = h->d_ts;
             attr.accessPolicyWindow.num_bytes = std::min<size_t>(hot, (size_t)max_window);
             attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)got / (double)attr.accessPolicyWindow.num_bytes);
+            if (getenv("ABNN_L2_RATIO")) attr.accessPolicyWindow.hitRatio = (float)atof(getenv("ABNN_L2_RATIO"));
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            attr.accessPolicyWindow.missProp = miss_normal ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
             if (cudaStreamSetAttribute(h->st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) h->l2_persist = got;
         }
         cudaGetLastError();

@@ -185,14 +185,13 @@ __device__ __forceinline__ u32 gated_path(const KParams& kp, const DevPtrs& d, c
 // fires (the common case), and no memory round trip between chain members. Exactly the serial
 // order for the events of one warp; across warps lastFired moves with atomicMax.
 // Returns bit0 = gated (weight written), bit1 = fired.
-__device__ __forceinline__ u32 chain_path(const KParams& kp, const DevPtrs& d, const PassConsts& pc, bool cand, u64 i,
-                                          u64 edge, u32 src, u32 dst, float w, u64 now)
+__device__ __forceinline__ u32 chain_resolve(const KParams& kp, const DevPtrs& d, const PassConsts& pc, bool cand, u64 i,
+                                             u64 edge, u32 src, u32 dst, float w, u64 now, u64 ld)
 {
     const unsigned cmask = __ballot_sync(0xffffffffu, cand);
     if (!cand) return 0;
     const unsigned lane  = threadIdx.x & 31;
     const unsigned peers = __match_any_sync(cmask, dst);
-    u64 ld = __ldcg(d.live + dst);                                                          // brain.metal:79
     const u64 eid = pc.event_base + i;
     Philox4 r{0, 0, 0, 0};
     if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_philox(kp, eid);
@@ -220,6 +219,13 @@ __device__ __forceinline__ u32 chain_path(const KParams& kp, const DevPtrs& d, c
     atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
     stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.w);
     return 3;
+}
+__device__ __forceinline__ u32 chain_path(const KParams& kp, const DevPtrs& d, const PassConsts& pc, bool cand, u64 i,
+                                          u64 edge, u32 src, u32 dst, float w, u64 now)
+{
+    u64 ld = 0;
+    if (cand) ld = __ldcg(d.live + dst);                                                    // brain.metal:79
+    return chain_resolve(kp, d, pc, cand, i, edge, src, dst, w, now, ld);
 }
 
 // Events that passed the pre-spike window: budgeted runs keep the turn-based path (the global spike
@@ -382,132 +388,208 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
 // ================================================================================================
 // Line sampler (sample_block = 8): one Philox draw = one 128-byte line of the table = 8 events.
 //
-// Each warp owns a ring of LINE_STAGES shared-memory stages. A stage holds one chunk = 32 lines = 256
-// events: lane L draws the line of group L and issues ONE cp.async.bulk (TMA bulk copy, UBLKCP) of that
-// line into the stage; the 32 copies of a chunk complete on the stage's mbarrier (expect_tx = bytes).
-// The warp refills a stage right after it consumed it, so LINE_STAGES-1 chunks (12 KB per warp) are
-// always in flight behind the one being processed: HBM latency is covered by the ring, not by
-// registers. The copies carry an L2 evict_first policy — the table is a stream and must not displace
-// the timestamp arrays that the access-policy window keeps resident.
-// Consumption: in step k lane l handles record (l & 7) of group 4k + (l >> 3), i.e. the warp reads 512
-// contiguous bytes of the stage (conflict-free LDS.128). The eight lastFired[src] reads of a lane are
-// issued back to back before any of them is used.
-constexpr int LINE_STAGES = 3;
+// Staging. Each warp owns a ring of LINE_STAGES shared-memory stages. A stage holds one chunk = 32
+// lines = 256 events: lane L draws the line of group L; the warp then copies the chunk with 8 cp.async
+// (LDGSTS.128) instructions, each moving 4 whole lines (8 lanes x 16 B per line, fully coalesced), one
+// commit group per chunk. The warp refills a stage right after it consumed it, so LINE_STAGES-1 chunks
+// (4 KB each) are always in flight behind the one being processed: HBM latency is covered by the ring,
+// not by registers or occupancy. The stream's access-policy window marks everything outside the
+// timestamp arrays as streaming, so the table does not displace them in L2.
+// (A first version moved each line with its own cp.async.bulk/mbarrier and measured the same as this
+// one: the copy engine was never the limit — instruction issue is, see profiles/r1_notes.md.)
+//
+// Consumption of a chunk, three phases:
+//   A  8 steps; in step k lane l holds record (l & 7) of group 4k + (l >> 3), i.e. the warp reads 512
+//      contiguous bytes of the stage. All eight lastFired[src] reads of a lane are issued back to back.
+//   B  8 steps: pre-spike window test (brain.metal:74), lastVisited RED once per run of equal
+//      destinations, lastFired[dst] reads of the events that pass ("candidates") issued back to back;
+//      then the refractory gate against those values (brain.metal:79): the events that are still open
+//      are COMPACTED — their 8-bit chunk-local index goes to a shared-memory queue in event order.
+//   C  ceil(open/32) dense steps over the queue: refractory gate again (now against the chunk's own
+//      fires too), release draw, plasticity, weight write-back, fire. The expensive path therefore runs
+//      with full warps instead of with the ~quarter of lanes that are open in a raw step; lastFired[dst]
+//      of step j+1 is fetched before step j is resolved. Same-destination candidates are ordered inside a step by chain_resolve and across the
+//      steps of a chunk by a small in-shared-memory list of the chunk's fires, so a warp's 256 events
+//      resolve exactly as in the serial order.
+#ifndef ABNN_LINE_STAGES
+#define ABNN_LINE_STAGES 2
+#endif
+#ifndef ABNN_LINE_MIN_CTAS
+#define ABNN_LINE_MIN_CTAS 2
+#endif
+constexpr int LINE_STAGES = ABNN_LINE_STAGES;
 constexpr int LINE_STAGE_BYTES = 32 * 128;
 constexpr int LINE_WARPS = 8;
-constexpr size_t LINE_SMEM = (size_t)LINE_WARPS * LINE_STAGES * (LINE_STAGE_BYTES + 32 * sizeof(u64) + sizeof(u64));
+constexpr u32 LINE_FIRE_CAP = 32;       // fires of one chunk kept in shared memory for the chunk's later steps
+constexpr size_t LINE_WARP_SMEM = (size_t)LINE_STAGES * (LINE_STAGE_BYTES + 32 * sizeof(u64)) + LINE_FIRE_CAP * (sizeof(u64) + sizeof(u32)) + 256;
+constexpr size_t LINE_SMEM = LINE_WARPS * LINE_WARP_SMEM;
 
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
-{
-    u32 done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar, u64 policy)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int VISITS>
-__global__ void __launch_bounds__(256, 2) k_traverse_line(const __grid_constant__ KParams kp, const DevPtrs d)
+__global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const __grid_constant__ KParams kp, const DevPtrs d)
 {
     constexpr int LOGB = 3, B = 8;
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* ring = line_smem + (size_t)warp * LINE_STAGES * LINE_STAGE_BYTES;
-    u64* meta = reinterpret_cast<u64*>(line_smem + (size_t)LINE_WARPS * LINE_STAGES * LINE_STAGE_BYTES) + warp * LINE_STAGES * 32;
-    u64* bars = reinterpret_cast<u64*>(line_smem + (size_t)LINE_WARPS * LINE_STAGES * (LINE_STAGE_BYTES + 32 * sizeof(u64))) + warp * LINE_STAGES;
+    // per-warp shared memory: ring | meta (line base | valid-1, per group) | fire list | candidate queue
+    unsigned char* ring = line_smem + warp * LINE_WARP_SMEM;
+    u64* meta   = reinterpret_cast<u64*>(ring + LINE_STAGES * LINE_STAGE_BYTES);
+    u64* fl_now = meta + LINE_STAGES * 32;
+    u32* fl_dst = reinterpret_cast<u32*>(fl_now + LINE_FIRE_CAP);
+    unsigned char* queue = reinterpret_cast<unsigned char*>(fl_dst + LINE_FIRE_CAP);
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < LINE_STAGES; ++s) mbar_init(bars + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
-    u64 policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     const PassConsts pc{d.sc->clock, d.sc->event_base, d.sc->tick_base, d.sc->reward, d.sc->rbar};
     u32 n_cand = 0, n_gated = 0, n_fired = 0;
-    const u32 rec = lane & (B - 1);
+    const u32 rec = lane & (B - 1), sub = lane >> LOGB;
+    const unsigned lt = (1u << lane) - 1u;
     const u64 warps_total = (u64)gridDim.x * LINE_WARPS, warp_global = (u64)blockIdx.x * LINE_WARPS + warp;
     const u64 n_chunks = (kp.count + 32ull * B - 1) / (32ull * B);
+    const bool per_event = kp.clock_mode != ABNN_CLOCK_PER_PASS;
 
-    // lane L draws the line of group L of chunk c and starts its copy into stage s
+    // lane L draws the line of group L of chunk c; the warp starts the copy of the 32 lines into stage s
     auto issue = [&](u64 c, int s) {
-        const u64 i0 = (c * 32 + lane) << LOGB;
-        u64 be = ~0ull;
-        u32 bytes = 0;
-        if (i0 < kp.count) {
-            const Philox4 r = event_philox(kp, pc.event_base + i0);
-            be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGB;
-            const u64 left = kp.n_local - be;                         // the table's last line may be short
-            bytes = (u32)(left < B ? left : B) * (u32)sizeof(abnn_synapse);
+        if (c < n_chunks) {
+            const u64 i0 = (c * 32 + lane) << LOGB;
+            u64 m = ~0ull;                                   // line base (multiple of 8) | (valid records - 1)
+            if (i0 < kp.count) {
+                const Philox4 r = event_philox(kp, pc.event_base + i0);
+                const u64 be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGB;
+                u64 valid = kp.n_local - be;                 // the table's last line may be short,
+                if (kp.count - i0 < valid) valid = kp.count - i0;   // and so may the pass's last group
+                m = be | ((valid < B ? valid : B) - 1);
+            }
+            meta[s * 32 + lane] = m;
+            unsigned char* dst = ring + (size_t)s * LINE_STAGE_BYTES + lane * 16;
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                const u64 mk = __shfl_sync(0xffffffffu, m, k * 4 + sub);
+                if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u))
+                    cp_async16(dst + k * 512, d.syn + (mk & ~7ull) + rec);
+            }
         }
-        meta[s * 32 + lane] = be;
-        const u32 total = __reduce_add_sync(0xffffffffu, bytes);
-        if (lane == 0) mbar_expect_tx(bars + s, total);
-        __syncwarp();
-        if (bytes) bulk_load(ring + (size_t)s * LINE_STAGE_BYTES + lane * 128, d.syn + be, bytes, bars + s, policy);
+        cp_async_commit();                                   // one group per ring slot, empty past the end
     };
 
     u64 c_next = warp_global;
 #pragma unroll
-    for (int s = 0; s < LINE_STAGES; ++s) {
-        if (c_next < n_chunks) issue(c_next, s);
-        c_next += warps_total;
-    }
-    u32 phases = 0;
+    for (int s = 0; s < LINE_STAGES - 1; ++s) { issue(c_next, s); c_next += warps_total; }
     int s = 0;
     for (u64 c = warp_global; c < n_chunks; c += warps_total) {
-        mbar_wait(bars + s, (phases >> s) & 1u);
-        phases ^= 1u << s;
-        const unsigned char* stage = ring + (size_t)s * LINE_STAGE_BYTES + lane * 16;
-        const u64* mb = meta + s * 32 + (lane >> LOGB);
+        {   // refill the slot consumed in the previous iteration, then wait for this iteration's chunk
+            const int sr = s == 0 ? LINE_STAGES - 1 : s - 1;
+            issue(c_next, sr);
+            c_next += warps_total;
+        }
+        cp_async_wait<LINE_STAGES - 1>();
+        __syncwarp();                                        // the other lanes' copies of this chunk have landed too
+        const unsigned char* stage = ring + (size_t)s * LINE_STAGE_BYTES;
+        const unsigned char* mine = stage + lane * 16;
+        const u64* mb = meta + s * 32;
+        const u64 ev0 = c * (32ull * B);                               // first event of the chunk
+        const u64 now0 = per_event ? pc.clock + ev0 * kp.world + kp.rank : pc.clock;
+        const u32 tick = per_event ? kp.world : 0u;                    // now(event ev0 + le) = now0 + le * tick
+        // two groups of the chunk drew the same line (small tables only): the later one must see the
+        // weights the earlier one wrote -> it re-reads them after a fence (bit g = group g repeats a line)
+        const u64 my_line = mb[lane];
+        const unsigned same = __match_any_sync(0xffffffffu, my_line);
+        const unsigned dupm = __ballot_sync(0xffffffffu, (u32)(my_line >> 32) != 0xFFFFFFFFu && (same & lt) != 0);
         u64 lp[B];
         u32 okm = 0;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {                                  // 8 lastFired[src] reads in flight per lane
-            const u64 be = mb[k * 4];
-            const u64 ev = ((c * 32 + k * 4 + (lane >> LOGB)) << LOGB) + rec;
-            const bool ok = be != ~0ull && ev < kp.count && be + rec < kp.n_local;
+        for (int k = 0; k < B; ++k) {                                  // A: 8 lastFired[src] reads in flight per lane
+            const u64 m = mb[k * 4 + sub];
             lp[k] = 0;
-            if (ok) {
+            if ((u32)(m >> 32) != 0xFFFFFFFFu && rec <= ((u32)m & 7u)) {
                 okm |= 1u << k;
-                lp[k] = __ldcg(d.view + *reinterpret_cast<const u32*>(stage + k * 512));   // brain.metal:73
+                lp[k] = __ldcg(d.view + *reinterpret_cast<const u32*>(mine + k * 512));    // brain.metal:73
             }
         }
+        u32 candm = 0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {                                  // B: window test, lastVisited, lastFired[dst] reads in flight
+            const bool ok = (okm >> k) & 1u;
+            const u32 dst = *reinterpret_cast<const u32*>(mine + k * 512 + 4);
+            const u64 now = now0 + (u64)((k * 32 + lane) * tick);
+            if (VISITS) visit(d, ok, dst, now);                                             // README.md:84
+            const bool cand = ok && (now - lp[k] <= kp.window_pre || (!kp.snapshot && lp[k] > now));   // brain.metal:74
+            lp[k] = now;
+            if (cand) { candm |= 1u << k; lp[k] = __ldcg(d.live + dst); }                   // brain.metal:79
+        }
+        n_cand += __popc(candm);
+        // In an active network most events pass the window and most of those are refractory. A fire can only
+        // move lastFired[dst] forward, so an event that is refractory against the value in memory stays
+        // refractory: drop those here and COMPACT the rest (in event order) for the dense steps.
+        u32 nC = 0;
 #pragma unroll
         for (int k = 0; k < B; ++k) {
-            const bool ok = (okm >> k) & 1u;
-            const uint4 sy = *reinterpret_cast<const uint4*>(stage + k * 512);             // brain.metal:70
-            const u64 ev = ((c * 32 + k * 4 + (lane >> LOGB)) << LOGB) + rec;
-            const u64 now = event_now(kp, pc.clock, ev);
-            if (VISITS) visit(d, ok, sy.y, now);                                            // README.md:84
-            const bool cand = ok && (now - lp[k] <= kp.window_pre || (!kp.snapshot && lp[k] > now));   // brain.metal:74
-            const u32 r = resolve_candidates(kp, d, pc, cand, ev, mb[k * 4] + rec, sy.x, sy.y, __uint_as_float(sy.z), now);
-            n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
+            const u64 now = now0 + (u64)((k * 32 + lane) * tick);
+            const u64 gap = lp[k] <= now ? now - lp[k] : lp[k] - now;
+            const bool open = ((candm >> k) & 1u) && gap > kp.refractory;                   // brain.metal:79-83
+            const unsigned cm = __ballot_sync(0xffffffffu, open);
+            if (open) queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
+            nC += __popc(cm);
+        }
+        __syncwarp();
+        // C: dense steps over the queue
+        u32 nf = 0;                                                    // fires of this chunk so far (warp-uniform)
+        bool spilled = false;                                          // fire list overflowed: later steps re-read lastFired
+        u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0); u64 ld = 0;
+        bool cand = lane < nC;
+        if (cand) {
+            le = queue[lane];
+            sy = *reinterpret_cast<const uint4*>(stage + le * 16);                          // brain.metal:70
+            ld = __ldcg(d.live + sy.y);                                                     // brain.metal:79
+        }
+#pragma unroll 1
+        for (u32 j = 0; j < nC; j += 32) {
+            u32 le_n = 0; uint4 sy_n = make_uint4(0, 0, 0, 0); u64 ld_n = 0;
+            const bool cand_n = j + 32 + lane < nC;
+            if (cand_n) {                                              // next step's record and lastFired[dst] on their way
+                le_n = queue[j + 32 + lane];
+                sy_n = *reinterpret_cast<const uint4*>(stage + le_n * 16);
+                ld_n = __ldcg(d.live + sy_n.y);
+            }
+            const u64 edge = (mb[le >> LOGB] & ~7ull) + (le & 7u);
+            const u64 ev = ev0 + le;
+            const u64 now = now0 + (u64)(le * tick);
+            float w = __uint_as_float(sy.z);
+            if (cand) {
+                if ((dupm >> (le >> LOGB)) & 1u) w = __ldcg(&d.syn[edge].w);
+                if (spilled) ld = __ldcg(d.live + sy.y);
+                else for (u32 f = 0; f < nf; ++f) {                    // fires of earlier steps of this chunk, in event order
+                    const u64 fn = fl_now[f];
+                    if (fl_dst[f] == sy.y && fn > ld) ld = fn;
+                }
+            }
+            u32 r;
+            if (kp.budget_on) r = cand ? gated_path(kp, d, pc, ev, edge, sy.x, sy.y, w, now) : 0u;
+            else r = chain_resolve(kp, d, pc, cand, ev, edge, sy.x, sy.y, w, now, ld);
+            n_gated += r & 1u; n_fired += r >> 1;
+            const unsigned fm = __ballot_sync(0xffffffffu, (r >> 1) != 0);
+            if (fm) {
+                const u32 at = nf + __popc(fm & lt);
+                if ((r >> 1) && at < LINE_FIRE_CAP) { fl_dst[at] = sy.y; fl_now[at] = now; }
+                nf += __popc(fm);
+                if (nf > LINE_FIRE_CAP) { nf = LINE_FIRE_CAP; spilled = true; }
+                __syncwarp();
+            }
+            if (dupm | (u32)spilled) __threadfence();                  // rare: make this step's writes visible to the re-reads
+            cand = cand_n; le = le_n; sy = sy_n; ld = ld_n;
         }
         __syncwarp();                                                   // every lane is done reading the stage
-        if (c_next < n_chunks) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(c_next, s);
-        }
-        c_next += warps_total;
         s = s + 1 == LINE_STAGES ? 0 : s + 1;
     }
+    cp_async_wait<0>();
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
 }
 

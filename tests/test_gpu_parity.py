@@ -216,7 +216,7 @@ def test_dst_sorted_table_bit_exact(mode):
     syn = random_graph(rng, n, N, 0.2, 1.0, dst_lo=16)
     pre = rng.integers(1, 40_000, N).astype(np.uint64)
     over = dict(n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, exec_mode=mode, sample_block=8,
-                table_order=capi.TABLE_DST_SORTED, window_pre=60_000, refractory=30_000, p_new=0.1, w_prune=0.21,
+                table_order=capi.TABLE_DST_SORTED, window_pre=250_000, refractory=30_000, p_new=0.1, w_prune=0.21,
                 syn_capacity=n + 20_000)
     b, o = pair(capi.PROFILE_NORTH_STAR, **over)
     for x in (b, o):
