@@ -426,18 +426,27 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     for (int i = 0; i < 8; ++i) CUH(cudaEventCreate(&h->timer[i]));
     for (int i = 0; i < RING; ++i) CUH(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     CUH(cudaMalloc(&h->d_syn, h->cap * sizeof(abnn_synapse)));
-    // timestamps: [view | visited | live] in one allocation so one access-policy window covers the
-    // arrays every event touches (view read, visited RED); LIVE src view: [live | visited].
-    // (Measured: a RED.MAX that misses L2 costs more than a read that misses — with [view | live] in
-    // the window instead, the pass is 30 % slower. profiles/r1_notes.md)
+    // timestamps in one allocation so that one access-policy window covers the hot arrays, hottest first:
+    //   SNAPSHOT view: [slack32 | visited | live | view]   LIVE view: [live | visited]
+    // slack32 is the per-pass 32-bit form of the snapshot that the line kernel's window gate reads
+    // (traversal.cu:k_build_slack); the 64-bit snapshot `view` serves the other kernels and the read-out.
+    // (Measured: a RED.MAX that misses L2 costs more than a read that misses — with lastVisited outside
+    // the window the pass is 30 % slower. profiles/r1_notes.md)
     const u64 npad = (h->npad + 31) & ~31ull;
     const bool snap = p.src_view == ABNN_SRC_SNAPSHOT;
-    const u64 arrays = snap ? 3 : 2;
-    CUH(cudaMalloc(&h->d_ts, arrays * npad * sizeof(u64)));
-    CUH(cudaMemsetAsync(h->d_ts, 0, arrays * npad * sizeof(u64), h->st));                      // brain.cpp:62-64
-    h->d.view = h->d_ts;
-    h->d.visited = h->d_ts + npad;
-    h->d.live = snap ? h->d_ts + 2 * npad : h->d_ts;
+    const u64 words = snap ? 7 : 4;                          // in units of npad * 4 bytes
+    CUH(cudaMalloc(&h->d_ts, words * npad * sizeof(u32)));
+    CUH(cudaMemsetAsync(h->d_ts, 0, words * npad * sizeof(u32), h->st));                       // brain.cpp:62-64
+    if (snap) {
+        h->d.slack = reinterpret_cast<u32*>(h->d_ts);
+        h->d.visited = h->d_ts + npad / 2;
+        h->d.live = h->d.visited + npad;
+        h->d.view = h->d.live + npad;
+    } else {
+        h->d.slack = nullptr;
+        h->d.live = h->d_ts; h->d.view = h->d_ts;
+        h->d.visited = h->d_ts + npad;
+    }
     h->d.syn = h->d_syn;
     CUH(cudaMalloc(&h->d.sc, sizeof(DevScalars)));
     {
@@ -473,8 +482,11 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (p.l2_persist && max_persist > 0 && max_window > 0) {
         const int n_arr = getenv("ABNN_L2_ARRAYS") ? atoi(getenv("ABNN_L2_ARRAYS")) : 2;
         const bool miss_normal = getenv("ABNN_L2_MISS") && atoi(getenv("ABNN_L2_MISS")) == 1;
-        const size_t hot = (size_t)std::min<u64>((u64)std::max(1, n_arr), arrays) * npad * sizeof(u64);
+        // default: slack32 + lastVisited (60 MB at 5M neurons) / LIVE view: lastFired + lastVisited
+        const u64 hot_words = snap ? (n_arr <= 1 ? 1 : n_arr == 2 ? 3 : 5) : (n_arr <= 1 ? 2 : 4);
+        const size_t hot = (size_t)hot_words * npad * sizeof(u32);
         size_t want = std::min<size_t>(hot, (size_t)max_persist);
+        if (getenv("ABNN_L2_CARVE_MAX")) want = (size_t)max_persist;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             size_t got = 0;
             cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
@@ -728,8 +740,13 @@ int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
 {
     RET(use(h));
     RET(refresh_counts(h));
-    const KParams kp = make_kparams(h, events);
+    KParams kp = make_kparams(h, events);
     if (stats) CU(cudaEventRecord(h->ev0, h->st));
+    if (h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && line_kernel_selected(kp) && kp.ticks < 0xFFFFFFF0ull &&
+        !getenv("ABNN_NO_SLACK")) {
+        kp.use_slack = 1;
+        CU(launch_build_slack(kp, h->d, h->st));
+    }
     switch (h->p.exec_mode) {
         case ABNN_EXEC_SERIAL:   CU(launch_traverse_serial(kp, h->d, h->st)); break;
         case ABNN_EXEC_PARALLEL: CU(launch_traverse_parallel(kp, h->d, h->sm_count, h->st)); break;

@@ -100,6 +100,7 @@ struct KParams {
     u64 n_blocks;                  // ceil(n_local / sample_block)
     float base_scale, a_ltp, a_ltd, w_min, w_max, eta_home, target_rate_hz, home_tick_hz, eta_reward, alpha_rbar;
     float p_new;
+    u32 use_slack;       // the line kernel reads DevPtrs::slack instead of the 64-bit snapshot
 };
 
 struct DevPtrs {
@@ -107,6 +108,7 @@ struct DevPtrs {
     u64* view;           // lastFired as seen for src reads (snapshot, or == live)
     u64* live;           // lastFired, authoritative for the owned dst range (indexed by global id)
     u64* visited;        // lastVisited
+    u32* slack;          // per-pass 32-bit form of the snapshot for the pre-spike window gate (line kernel), or null
     DevScalars* sc;
     GrowCand* grow;
 };

@@ -386,66 +386,100 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
 
 
 // ================================================================================================
+// Pre-spike window gate in 32 bits. With the SNAPSHOT src view the gate of event e (brain.metal:73-77)
+//     now(e) - lastFired_snapshot[src] <= window_pre,      now(e) = clock + t(e),  0 <= t < ticks
+// depends on src only through  v[src] = window_pre - (clock - lastFired_snapshot[src]) + 1 :
+// the event passes iff t(e) < v[src]. v is rebuilt before every pass (one streaming sweep over the
+// snapshot, 12 bytes per neuron) and clamped to 32 bits: 0 = never passes in this pass, >= ticks =
+// always passes. The 5M-neuron gate array that every event reads is then 20 MB instead of 40 MB, which
+// is what lets it stay L2-resident next to lastVisited/lastFired under the 1B-synapse stream.
+// 0xFFFFFFFF marks the (pathological) neurons whose snapshot lies in the future of the pass start;
+// for those the kernel falls back to the exact 64-bit test.
+constexpr u32 SLACK_EXACT = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(256) k_build_slack(const __grid_constant__ KParams kp, const DevPtrs d)
+{
+    const u64 clock = d.sc->clock;
+    for (u64 n = (u64)blockIdx.x * blockDim.x + threadIdx.x; n < kp.n_neuron; n += (u64)gridDim.x * blockDim.x) {
+        const u64 lp = d.view[n];
+        u32 v;
+        if (lp > clock) v = SLACK_EXACT;
+        else {
+            const u64 age = clock - lp;
+            if (age > kp.window_pre) v = 0;
+            else { const u64 room = kp.window_pre - age; v = room >= 0xFFFFFFFDull ? 0xFFFFFFFEu : (u32)room + 1u; }
+        }
+        d.slack[n] = v;
+    }
+}
+cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, cudaStream_t st)
+{
+    u64 blocks = (kp.n_neuron + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (!blocks) return cudaSuccess;
+    k_build_slack<<<(unsigned)blocks, 256, 0, st>>>(kp, d);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
 // Line sampler (sample_block = 8): one Philox draw = one 128-byte line of the table = 8 events.
 //
-// Staging. Each warp owns a ring of LINE_STAGES shared-memory stages. A stage holds one chunk = 32
-// lines = 256 events: lane L draws the line of group L; the warp then copies the chunk with 8 cp.async
-// (LDGSTS.128) instructions, each moving 4 whole lines (8 lanes x 16 B per line, fully coalesced), one
-// commit group per chunk. The warp refills a stage right after it consumed it, so LINE_STAGES-1 chunks
-// (4 KB each) are always in flight behind the one being processed: HBM latency is covered by the ring,
-// not by registers or occupancy. The stream's access-policy window marks everything outside the
-// timestamp arrays as streaming, so the table does not displace them in L2.
-// (A first version moved each line with its own cp.async.bulk/mbarrier and measured the same as this
-// one: the copy engine was never the limit — instruction issue is, see profiles/r1_notes.md.)
-//
-// Consumption of a chunk, three phases:
+// A warp walks chunks of 32 lines = 256 events. Lane L draws the line of group L; the warp copies the
+// chunk into its 4 KB shared-memory stage with 8 cp.async (LDGSTS.128) instructions, each moving 4 whole
+// lines (8 lanes x 16 B per line, fully coalesced), draws the lines of its NEXT chunk while the copy is
+// in flight, and then consumes the stage in three phases:
 //   A  8 steps; in step k lane l holds record (l & 7) of group 4k + (l >> 3), i.e. the warp reads 512
-//      contiguous bytes of the stage. All eight lastFired[src] reads of a lane are issued back to back.
+//      contiguous bytes of the stage. The pre-spike gate word of src (32-bit slack, k_build_slack) and
+//      lastFired[dst] of all 8 steps are requested back to back: 16 independent L2 reads per lane.
 //   B  8 steps: pre-spike window test (brain.metal:74), lastVisited RED once per run of equal
-//      destinations, lastFired[dst] reads of the events that pass ("candidates") issued back to back;
-//      then the refractory gate against those values (brain.metal:79): the events that are still open
-//      are COMPACTED — their 8-bit chunk-local index goes to a shared-memory queue in event order.
-//   C  ceil(open/32) dense steps over the queue: refractory gate again (now against the chunk's own
-//      fires too), release draw, plasticity, weight write-back, fire. The expensive path therefore runs
-//      with full warps instead of with the ~quarter of lanes that are open in a raw step; lastFired[dst]
-//      of step j+1 is fetched before step j is resolved. Same-destination candidates are ordered inside a step by chain_resolve and across the
-//      steps of a chunk by a small in-shared-memory list of the chunk's fires, so a warp's 256 events
-//      resolve exactly as in the serial order.
-#ifndef ABNN_LINE_STAGES
-#define ABNN_LINE_STAGES 2
-#endif
+//      destinations, refractory gate against the value read in A (brain.metal:79): the events that are
+//      still open are COMPACTED — their 8-bit chunk-local index goes to a shared-memory queue in event
+//      order. (In an active network most events pass the window and most of those are refractory; a fire
+//      only moves lastFired[dst] forward, so an event that is refractory against memory stays refractory.)
+//   C  ceil(open/32) dense steps over the queue: refractory gate again (now also against the chunk's own
+//      fires), release draw, plasticity, weight write-back, fire. The expensive path runs with full warps
+//      instead of with the ~quarter of lanes that are open in a raw step; lastFired[dst] of step j+1 is
+//      fetched before step j is resolved. Same-destination events are ordered inside a step by
+//      chain_resolve and across the steps of a chunk by a small shared-memory list of the chunk's
+//      fires, so a warp's 256 events resolve exactly as in the serial order.
+//
+// Shared memory is kept to 4.5 KB per warp on purpose. Measured on B200 (profiles/r1_notes.md): the
+// gathers of this kernel are limited by the L1's capacity to track outstanding misses, i.e. by what the
+// shared-memory carve-out leaves of the 228 KB array. A 3-deep ring (13.5 KB/warp, 16 warps) ran at
+// 3.4 ms/pass, a 2-deep ring 2.1 ms, this single stage with 24 warps 1.7 ms; forcing the carve-out to
+// 100 % shared memory took the same code from 2.1 to 3.9 ms. HBM latency is hidden across warps.
+// (Also measured and dropped: one cp.async.bulk (TMA) + mbarrier per line with an L2 evict_first
+// policy — 7 % slower than LDGSTS at equal depth.)
 #ifndef ABNN_LINE_MIN_CTAS
-#define ABNN_LINE_MIN_CTAS 2
+#define ABNN_LINE_MIN_CTAS 3
 #endif
-constexpr int LINE_STAGES = ABNN_LINE_STAGES;
 constexpr int LINE_STAGE_BYTES = 32 * 128;
 constexpr int LINE_WARPS = 8;
-constexpr u32 LINE_FIRE_CAP = 32;       // fires of one chunk kept in shared memory for the chunk's later steps
-constexpr size_t LINE_WARP_SMEM = (size_t)LINE_STAGES * (LINE_STAGE_BYTES + 32 * sizeof(u64)) + LINE_FIRE_CAP * (sizeof(u64) + sizeof(u32)) + 256;
+constexpr u32 LINE_FIRE_CAP = 16;       // fires of one chunk kept in shared memory for the chunk's later steps
+constexpr size_t LINE_WARP_SMEM = LINE_STAGE_BYTES + 256 + LINE_FIRE_CAP * (sizeof(u64) + sizeof(u32)) + 64;   // 4608
 constexpr size_t LINE_SMEM = LINE_WARPS * LINE_WARP_SMEM;
 
-__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
+__device__ __forceinline__ void cp_async16(u32 dst_smem, const void* src_gmem)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int VISITS>
+template <int VISITS, int SLACK>
 __global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const __grid_constant__ KParams kp, const DevPtrs d)
 {
     constexpr int LOGB = 3, B = 8;
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp shared memory: ring | meta (line base | valid-1, per group) | fire list | candidate queue
-    unsigned char* ring = line_smem + warp * LINE_WARP_SMEM;
-    u64* meta   = reinterpret_cast<u64*>(ring + LINE_STAGES * LINE_STAGE_BYTES);
-    u64* fl_now = meta + LINE_STAGES * 32;
+    // per-warp shared memory: stage | candidate queue | fire list
+    unsigned char* stage = line_smem + warp * LINE_WARP_SMEM;
+    unsigned char* queue = stage + LINE_STAGE_BYTES;
+    u64* fl_now = reinterpret_cast<u64*>(queue + 256);
     u32* fl_dst = reinterpret_cast<u32*>(fl_now + LINE_FIRE_CAP);
-    unsigned char* queue = reinterpret_cast<unsigned char*>(fl_dst + LINE_FIRE_CAP);
+    const unsigned char* mine = stage + lane * 16;
+    const u32 mine_addr = (u32)__cvta_generic_to_shared(mine);
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const PassConsts pc{d.sc->clock, d.sc->event_base, d.sc->tick_base, d.sc->reward, d.sc->rbar};
@@ -454,95 +488,104 @@ __global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const
     const unsigned lt = (1u << lane) - 1u;
     const u64 warps_total = (u64)gridDim.x * LINE_WARPS, warp_global = (u64)blockIdx.x * LINE_WARPS + warp;
     const u64 n_chunks = (kp.count + 32ull * B - 1) / (32ull * B);
-    const bool per_event = kp.clock_mode != ABNN_CLOCK_PER_PASS;
+    const u32 tick = kp.clock_mode != ABNN_CLOCK_PER_PASS ? kp.world : 0u;   // now(event i) = clock + i * world + rank | clock
 
-    // lane L draws the line of group L of chunk c; the warp starts the copy of the 32 lines into stage s
-    auto issue = [&](u64 c, int s) {
-        if (c < n_chunks) {
-            const u64 i0 = (c * 32 + lane) << LOGB;
-            u64 m = ~0ull;                                   // line base (multiple of 8) | (valid records - 1)
-            if (i0 < kp.count) {
-                const Philox4 r = event_philox(kp, pc.event_base + i0);
-                const u64 be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGB;
-                u64 valid = kp.n_local - be;                 // the table's last line may be short,
-                if (kp.count - i0 < valid) valid = kp.count - i0;   // and so may the pass's last group
-                m = be | ((valid < B ? valid : B) - 1);
-            }
-            meta[s * 32 + lane] = m;
-            unsigned char* dst = ring + (size_t)s * LINE_STAGE_BYTES + lane * 16;
-#pragma unroll
-            for (int k = 0; k < B; ++k) {
-                const u64 mk = __shfl_sync(0xffffffffu, m, k * 4 + sub);
-                if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u))
-                    cp_async16(dst + k * 512, d.syn + (mk & ~7ull) + rec);
-            }
-        }
-        cp_async_commit();                                   // one group per ring slot, empty past the end
+    // lane L draws the line of group L of chunk c: line base (a multiple of 8) | (valid records - 1), ~0 = none
+    auto draw = [&](u64 c) -> u64 {
+        const u64 i0 = (c * 32 + lane) << LOGB;
+        if (c >= n_chunks || i0 >= kp.count) return ~0ull;
+        const Philox4 r = event_philox(kp, pc.event_base + i0);
+        const u64 be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGB;
+        u64 valid = kp.n_local - be;                         // the table's last line may be short,
+        if (kp.count - i0 < valid) valid = kp.count - i0;    // and so may the pass's last group
+        return be | ((valid < B ? valid : B) - 1);
     };
 
-    u64 c_next = warp_global;
-#pragma unroll
-    for (int s = 0; s < LINE_STAGES - 1; ++s) { issue(c_next, s); c_next += warps_total; }
-    int s = 0;
+    u64 m = draw(warp_global);
     for (u64 c = warp_global; c < n_chunks; c += warps_total) {
-        {   // refill the slot consumed in the previous iteration, then wait for this iteration's chunk
-            const int sr = s == 0 ? LINE_STAGES - 1 : s - 1;
-            issue(c_next, sr);
-            c_next += warps_total;
-        }
-        cp_async_wait<LINE_STAGES - 1>();
-        __syncwarp();                                        // the other lanes' copies of this chunk have landed too
-        const unsigned char* stage = ring + (size_t)s * LINE_STAGE_BYTES;
-        const unsigned char* mine = stage + lane * 16;
-        const u64* mb = meta + s * 32;
-        const u64 ev0 = c * (32ull * B);                               // first event of the chunk
-        const u64 now0 = per_event ? pc.clock + ev0 * kp.world + kp.rank : pc.clock;
-        const u32 tick = per_event ? kp.world : 0u;                    // now(event ev0 + le) = now0 + le * tick
-        // two groups of the chunk drew the same line (small tables only): the later one must see the
-        // weights the earlier one wrote -> it re-reads them after a fence (bit g = group g repeats a line)
-        const u64 my_line = mb[lane];
-        const unsigned same = __match_any_sync(0xffffffffu, my_line);
-        const unsigned dupm = __ballot_sync(0xffffffffu, (u32)(my_line >> 32) != 0xFFFFFFFFu && (same & lt) != 0);
-        u64 lp[B];
+        // ---- stage the chunk ------------------------------------------------------------------------
         u32 okm = 0;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {                                  // A: 8 lastFired[src] reads in flight per lane
-            const u64 m = mb[k * 4 + sub];
-            lp[k] = 0;
-            if ((u32)(m >> 32) != 0xFFFFFFFFu && rec <= ((u32)m & 7u)) {
+        for (int k = 0; k < B; ++k) {
+            const u64 mk = __shfl_sync(0xffffffffu, m, k * 4 + sub);
+            if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u)) {
                 okm |= 1u << k;
-                lp[k] = __ldcg(d.view + *reinterpret_cast<const u32*>(mine + k * 512));    // brain.metal:73
+                cp_async16(mine_addr + k * 512, d.syn + (mk & ~7ull) + rec);
+            }
+        }
+        cp_async_commit();
+        // two groups of the chunk drew the same line (small tables only): the later one must see the
+        // weights the earlier one wrote -> it re-reads them after a fence (bit g = group g repeats a line)
+        const unsigned same = __match_any_sync(0xffffffffu, m);
+        const unsigned dupm = __ballot_sync(0xffffffffu, m != ~0ull && (same & lt) != 0);
+        const u64 m_next = draw(c + warps_total);            // ALU work under the copy's latency
+        const u64 ev0 = c * (32ull * B);                     // first event of the chunk
+        const u64 now0 = tick ? pc.clock + ev0 * kp.world + kp.rank : pc.clock;
+        const u32 t0 = (u32)(now0 - pc.clock);               // SLACK: ticks fit 32 bits (abnn_run_pass)
+        cp_async_wait<0>();
+        __syncwarp();                                        // the other lanes' copies have landed too
+
+        // ---- A: gate and lastFired[dst] reads in flight ---------------------------------------------
+        u64 ts[B];                                           // lastFired[dst] (SLACK) / lastFired[src], then [dst]
+        u32 gate[B];                                         // SLACK: v[src]
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            ts[k] = 0; gate[k] = 0;
+            if ((okm >> k) & 1u) {
+                const uint2 sd = *reinterpret_cast<const uint2*>(mine + k * 512);
+                if (SLACK) {
+                    gate[k] = __ldcg(d.slack + sd.x);                                       // brain.metal:73 (32-bit form)
+                    ts[k] = __ldcg(d.live + sd.y);                                          // brain.metal:79
+                } else {
+                    ts[k] = __ldcg(d.view + sd.x);                                          // brain.metal:73
+                }
             }
         }
         u32 candm = 0;
+        if (SLACK) {
+            u32 exact = 0;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {                                  // B: window test, lastVisited, lastFired[dst] reads in flight
-            const bool ok = (okm >> k) & 1u;
-            const u32 dst = *reinterpret_cast<const u32*>(mine + k * 512 + 4);
-            const u64 now = now0 + (u64)((k * 32 + lane) * tick);
-            if (VISITS) visit(d, ok, dst, now);                                             // README.md:84
-            const bool cand = ok && (now - lp[k] <= kp.window_pre || (!kp.snapshot && lp[k] > now));   // brain.metal:74
-            lp[k] = now;
-            if (cand) { candm |= 1u << k; lp[k] = __ldcg(d.live + dst); }                   // brain.metal:79
+            for (int k = 0; k < B; ++k) {
+                candm |= (u32)(((okm >> k) & 1u) && t0 + (k * 32 + lane) * tick < gate[k]) << k;   // brain.metal:74
+                exact |= (u32)(gate[k] == SLACK_EXACT) << k;
+            }
+            if (__any_sync(0xffffffffu, exact & okm)) {      // snapshot in the future of the pass start: exact 64-bit test
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    if (((exact & okm) >> k) & 1u) {
+                        const u64 now = now0 + (u64)((k * 32 + lane) * tick);
+                        const bool cand = now - __ldcg(d.view + *reinterpret_cast<const u32*>(mine + k * 512)) <= kp.window_pre;
+                        candm = (candm & ~(1u << k)) | ((u32)cand << k);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < B; ++k) {                    // 64-bit gate: window test, then lastFired[dst] reads in flight
+                const u64 now = now0 + (u64)((k * 32 + lane) * tick);
+                const bool cand = ((okm >> k) & 1u) && (now - ts[k] <= kp.window_pre || (!kp.snapshot && ts[k] > now));   // brain.metal:74
+                ts[k] = now;
+                if (cand) { candm |= 1u << k; ts[k] = __ldcg(d.live + *reinterpret_cast<const u32*>(mine + k * 512 + 4)); }   // brain.metal:79
+            }
         }
         n_cand += __popc(candm);
-        // In an active network most events pass the window and most of those are refractory. A fire can only
-        // move lastFired[dst] forward, so an event that is refractory against the value in memory stays
-        // refractory: drop those here and COMPACT the rest (in event order) for the dense steps.
+
+        // ---- B: lastVisited, refractory gate, compaction of the open events ----------------------------
         u32 nC = 0;
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             const u64 now = now0 + (u64)((k * 32 + lane) * tick);
-            const u64 gap = lp[k] <= now ? now - lp[k] : lp[k] - now;
+            if (VISITS) visit(d, (okm >> k) & 1u, *reinterpret_cast<const u32*>(mine + k * 512 + 4), now);   // README.md:84
+            const u64 gap = ts[k] <= now ? now - ts[k] : ts[k] - now;
             const bool open = ((candm >> k) & 1u) && gap > kp.refractory;                   // brain.metal:79-83
             const unsigned cm = __ballot_sync(0xffffffffu, open);
             if (open) queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
             nC += __popc(cm);
         }
         __syncwarp();
-        // C: dense steps over the queue
-        u32 nf = 0;                                                    // fires of this chunk so far (warp-uniform)
-        bool spilled = false;                                          // fire list overflowed: later steps re-read lastFired
+
+        // ---- C: dense steps over the queue ----------------------------------------------------------------
+        u32 nf = 0;                                          // fires of this chunk so far (warp-uniform)
+        bool spilled = false;                                // fire list overflowed: later steps re-read lastFired
         u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0); u64 ld = 0;
         bool cand = lane < nC;
         if (cand) {
@@ -554,19 +597,19 @@ __global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const
         for (u32 j = 0; j < nC; j += 32) {
             u32 le_n = 0; uint4 sy_n = make_uint4(0, 0, 0, 0); u64 ld_n = 0;
             const bool cand_n = j + 32 + lane < nC;
-            if (cand_n) {                                              // next step's record and lastFired[dst] on their way
+            if (cand_n) {                                    // next step's record and lastFired[dst] on their way
                 le_n = queue[j + 32 + lane];
                 sy_n = *reinterpret_cast<const uint4*>(stage + le_n * 16);
                 ld_n = __ldcg(d.live + sy_n.y);
             }
-            const u64 edge = (mb[le >> LOGB] & ~7ull) + (le & 7u);
+            const u64 edge = (__shfl_sync(0xffffffffu, m, le >> LOGB) & ~7ull) + (le & 7u);
             const u64 ev = ev0 + le;
             const u64 now = now0 + (u64)(le * tick);
             float w = __uint_as_float(sy.z);
             if (cand) {
                 if ((dupm >> (le >> LOGB)) & 1u) w = __ldcg(&d.syn[edge].w);
                 if (spilled) ld = __ldcg(d.live + sy.y);
-                else for (u32 f = 0; f < nf; ++f) {                    // fires of earlier steps of this chunk, in event order
+                else for (u32 f = 0; f < nf; ++f) {          // fires of earlier steps of this chunk, in event order
                     const u64 fn = fl_now[f];
                     if (fl_dst[f] == sy.y && fn > ld) ld = fn;
                 }
@@ -583,13 +626,12 @@ __global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const
                 if (nf > LINE_FIRE_CAP) { nf = LINE_FIRE_CAP; spilled = true; }
                 __syncwarp();
             }
-            if (dupm | (u32)spilled) __threadfence();                  // rare: make this step's writes visible to the re-reads
+            if (dupm | (u32)spilled) __threadfence();        // rare: make this step's writes visible to the re-reads
             cand = cand_n; le = le_n; sy = sy_n; ld = ld_n;
         }
-        __syncwarp();                                                   // every lane is done reading the stage
-        s = s + 1 == LINE_STAGES ? 0 : s + 1;
+        __syncwarp();                                        // every lane is done with the stage
+        m = m_next;
     }
-    cp_async_wait<0>();
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
 }
 
@@ -642,26 +684,28 @@ static cudaError_t launch_parallel_t(const KParams& kp, const DevPtrs& d, int sm
 }
 
 
-template <int VISITS>
+template <int VISITS, int SLACK>
 static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_traverse_line<VISITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
         if (e != cudaSuccess) return e;
+        if (getenv("ABNN_LINE_CARVEOUT"))      // measurements only: shared-memory share of the L1/shared array, percent
+            cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("ABNN_LINE_CARVEOUT")));
         configured = true;
     }
     if (!kp.count || !kp.n_local) return cudaSuccess;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line<VISITS>, 256, LINE_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line<VISITS, SLACK>, 256, LINE_SMEM);
     if (per_sm < 1) per_sm = 1;
     if (bps > 0 && bps < per_sm) per_sm = bps;
     const u64 chunks = (kp.count + 255) / 256;
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
     if (grid > chunks / (LINE_WARPS * 16) + 1) grid = chunks / (LINE_WARPS * 16) + 1;   // in-flight window <= 1/16 of the pass
-    k_traverse_line<VISITS><<<(unsigned)grid, 256, LINE_SMEM, st>>>(kp, d);
+    k_traverse_line<VISITS, SLACK><<<(unsigned)grid, 256, LINE_SMEM, st>>>(kp, d);
     return cudaGetLastError();
 }
 
@@ -693,11 +737,18 @@ static cudaError_t launch_block(const KParams& kp, const DevPtrs& d, int sm_coun
     }
 }
 
+bool line_kernel_selected(const KParams& kp)
+{
+    static const bool legacy_block = getenv("ABNN_TRAV_LEGACY_BLOCK") != nullptr;      // A/B measurements only
+    return kp.sampler == ABNN_SAMPLER_PHILOX && kp.sample_block == 8 && !legacy_block;
+}
 cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     const bool ph = kp.sampler == ABNN_SAMPLER_PHILOX, vis = kp.track_visits != 0;
-    static const bool legacy_block = getenv("ABNN_TRAV_LEGACY_BLOCK") != nullptr;      // A/B measurements only
-    if (ph && kp.sample_block == 8 && !legacy_block) return vis ? launch_line<1>(kp, d, sm_count, st) : launch_line<0>(kp, d, sm_count, st);
+    if (line_kernel_selected(kp)) {
+        if (kp.use_slack) return vis ? launch_line<1, 1>(kp, d, sm_count, st) : launch_line<0, 1>(kp, d, sm_count, st);
+        return vis ? launch_line<1, 0>(kp, d, sm_count, st) : launch_line<0, 0>(kp, d, sm_count, st);
+    }
     if (ph && kp.sample_block > 1) return vis ? launch_block<1>(kp, d, sm_count, st) : launch_block<0>(kp, d, sm_count, st);
     if (ph && vis)  return launch_parallel_t<ABNN_SAMPLER_PHILOX, 1>(kp, d, sm_count, st);
     if (ph && !vis) return launch_parallel_t<ABNN_SAMPLER_PHILOX, 0>(kp, d, sm_count, st);
