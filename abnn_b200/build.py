@@ -84,5 +84,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_host_tests() -> str:
+    """Compile tests/host_cpp/engine_parity.cpp (host C++17 over include/abnn_brain.hpp) against the library."""
+    root = os.path.abspath(os.path.join(HERE, ".."))
+    src = os.path.join(root, "tests", "host_cpp", "engine_parity.cpp")
+    exe = os.path.join(root, "tests", "host_cpp", "engine_parity")
+    lib = build()
+    deps = [src, os.path.join(root, "include", "abnn_brain.hpp"), os.path.join(root, "include", "abnn.h"), lib]
+    if os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
+        return exe
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(root, "include"), src, "-o", exe,
+           "-L", HERE, "-labnn_b200", "-Wl,-rpath," + HERE, "-pthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed on engine_parity.cpp:\n{r.stdout}")
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

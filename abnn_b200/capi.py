@@ -139,6 +139,26 @@ class AbnnError(RuntimeError):
         self.status = status
 
 
+def _preload_nccl() -> None:
+    """libabnn_b200.so needs libnccl.so.2 (>= 2.27). A process gets ONE library per soname: if a PyTorch
+    wheel with its own, newer NCCL is installed, load that copy first so that a later `import torch`
+    (bench.py, abnn_b200.distributed) finds the symbols it was built against. Without such a wheel the
+    system libnccl is used. PyTorch itself is never imported here."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia")
+    except Exception:
+        spec = None
+    for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(root, "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load() -> C.CDLL:
     """Load libabnn_b200.so (built in-tree by __graft_entry__.build()). Raises if missing."""
     global _lib
@@ -149,6 +169,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: the CUDA library has not been built. Run "
             "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
             "abnn_b200 has no CPU fallback.")
+    _preload_nccl()
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol

@@ -42,7 +42,7 @@ HBM_FALLBACK_GBS = 6650.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hidden", type=int, default=5_000_000)
@@ -58,9 +58,19 @@ def parse():
     ap.add_argument("--no-visits", action="store_true")
     ap.add_argument("--no-l2-persist", action="store_true")
     ap.add_argument("--cpu-syn", type=int, default=100_000_000)
-    ap.add_argument("--cpu-events", type=int, default=20_000_000)
+    ap.add_argument("--cpu-events", type=int, default=150_000_000)
     ap.add_argument("--skip-cpu", action="store_true")
     return ap.parse_args()
+
+
+def ncu_traffic(workload_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
+    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return t["dram_bytes_per_launch"] if t.get("workload_key") == workload_key else None
+    except Exception:
+        return None
 
 
 def peaks():
@@ -308,6 +318,7 @@ def main():
         peak, peak_kind = peaks()
         # per-GPU roofline of the traversal kernel: this rank's events per launch
         ev_per_launch = evs / (min(K, 10) * world)
+        wkey = f"{args.hidden}/{args.syn}/{args.events}/{args.sampler}/b{args.block}/{args.table_order}/{args.src_view}/w{world}"
         achieved = ev_per_launch * b_alg / (trav_mean * 1e-3) / 1e9
         line = {
             "metric": "synaptic events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -321,12 +332,15 @@ def main():
                        "l2_persist_bytes": int(info.l2_persist_bytes)},
             "gated_fraction": g, "fire_fraction": fired / max(1.0, evs),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_traverse_parallel",
+                         "traffic": ncu_traffic(wkey), "peak_kind": peak_kind,
+                         "kernel": "k_traverse_line" if (args.sampler == "philox" and args.block == 8) else "k_traverse_parallel",
                          "kernel_ms": trav_mean, "alg_bytes_per_event": b_alg,
                          "sector_level_frac": ev_per_launch * (32.0 + 32.0 * g) / (trav_mean * 1e-3) / 1e9 / peak},
             "e2e": {"value": args.events * K / e2e_s, "unit": "events/s",
                     "h2d_bytes_per_step": int(3 * N_IN * 4), "d2h_bytes_per_step": int(N_OUT * 4)},
-            "gpu_launches": 5 * K,
+            # per step: k_inject, k_teacher, k_build_slack, traversal kernel, k_end_pass, k_readout (+ the snapshot copy /
+            # NCCL allgather, not counted)
+            "gpu_launches": 6 * K,
             "clocks": clocks,
         }
         if world == 1 and not args.skip_cpu:
