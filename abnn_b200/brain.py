@@ -98,6 +98,13 @@ class Brain:
     def load(self, path: str):
         capi.check(self.lib.abnn_load_bnn(self.h, path.encode()), "abnn_load_bnn")
 
+    def save_state(self, path: str):
+        """.bnn v2: records + timestamps + clock + r-bar + read-out state, for exact resume."""
+        capi.check(self.lib.abnn_save_state(self.h, path.encode()), "abnn_save_state")
+
+    def load_state(self, path: str):
+        capi.check(self.lib.abnn_load_state(self.h, path.encode()), "abnn_load_state")
+
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         capi.check(self.lib.abnn_comm_init(self.h, buf), "abnn_comm_init")

@@ -108,6 +108,9 @@ SIGNATURES = {
     "abnn_download_synapses": (C.c_int, [_H, C.c_void_p, C.c_uint64, _P(C.c_uint64)]),
     "abnn_save_bnn": (C.c_int, [_H, C.c_char_p]),
     "abnn_load_bnn": (C.c_int, [_H, C.c_char_p]),
+    "abnn_save_state": (C.c_int, [_H, C.c_char_p]),
+    "abnn_load_state": (C.c_int, [_H, C.c_char_p]),
+    "abnn_params_from_manifest": (C.c_int, [C.c_char_p, _P(Params), _P(C.c_uint64), _P(C.c_uint64)]),
     "abnn_inject_inputs": (C.c_int, [_H, C.c_void_p, C.c_uint32, C.c_float]),
     "abnn_teacher_force": (C.c_int, [_H, C.c_void_p, C.c_uint32, C.c_float]),
     "abnn_set_reward": (C.c_int, [_H, C.c_float]),
@@ -191,3 +194,11 @@ def default_params(profile: int = PROFILE_NORTH_STAR) -> Params:
     p = Params()
     check(load().abnn_default_params(C.byref(p), profile), "abnn_default_params")
     return p
+
+
+def params_from_manifest(path: str, profile: int = PROFILE_NORTH_STAR):
+    """Defaults of `profile` overridden by a flat-key YAML manifest. Returns (params, steps, tau_LTD)."""
+    p = default_params(profile)
+    steps, tau_ltd = C.c_uint64(), C.c_uint64()
+    check(load().abnn_params_from_manifest(path.encode(), C.byref(p), C.byref(steps), C.byref(tau_ltd)), "abnn_params_from_manifest")
+    return p, steps.value, tau_ltd.value

@@ -2,6 +2,9 @@
 // Owns the device state that the reference's `Brain` owns as Metal buffers (brain.cpp:52-69) and
 // sequences the kernels of one pass on the handle's stream (Brain::encode_traversal, brain.cpp:87-122).
 #include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -693,6 +696,216 @@ int abnn_load_bnn(abnn_handle* h, const char* path)
     std::fclose(f);
     h->n_local = n; h->n_local_all.assign(1, n); h->counts_dirty = false;
     RET(sort_table(h));
+    return 0;
+}
+
+// ---- .bnn v2: exact resume ------------------------------------------------------------------------
+namespace {
+struct Bnn2Header {
+    char     magic[4];             // "BNN2"
+    uint32_t version, scalars_size, params_size;
+    uint64_t n_local, n_neuron, n_syn_global;
+    uint32_t rank, world, n_output, fir_size;
+    uint32_t grow_count, snapshot;
+};
+bool put(FILE* f, const void* p, size_t n) { return n == 0 || std::fwrite(p, 1, n, f) == n; }
+bool get(FILE* f, void* p, size_t n) { return n == 0 || std::fread(p, 1, n, f) == n; }
+// device -> file / file -> device through a bounded host buffer
+int dev_to_file(abnn_handle* h, FILE* f, const void* d, size_t bytes, std::vector<char>& buf)
+{
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+        const size_t m = std::min(buf.size(), bytes - off);
+        CU(cudaMemcpyAsync(buf.data(), (const char*)d + off, m, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        if (!put(f, buf.data(), m)) return fail(ABNN_ERR_IO, "short write");
+    }
+    return 0;
+}
+int file_to_dev(abnn_handle* h, FILE* f, void* d, size_t bytes, std::vector<char>& buf)
+{
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+        const size_t m = std::min(buf.size(), bytes - off);
+        if (!get(f, buf.data(), m)) return fail(ABNN_ERR_IO, "short read");
+        CU(cudaMemcpyAsync((char*)d + off, buf.data(), m, cudaMemcpyHostToDevice, h->st));
+        CU(cudaStreamSynchronize(h->st));
+    }
+    return 0;
+}
+}  // namespace
+
+int abnn_save_state(abnn_handle* h, const char* path)
+{
+    RET(use(h));
+    if (!path) return fail(ABNN_ERR_INVALID, "null path");
+    RET(refresh_counts(h));
+    DevScalars sc; RET(read_scalars(h, &sc));
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(ABNN_ERR_IO, std::string("cannot open for writing: ") + path);
+    Bnn2Header hd{};
+    std::memcpy(hd.magic, "BNN2", 4);
+    hd.version = 2; hd.scalars_size = sizeof(DevScalars); hd.params_size = sizeof(abnn_params);
+    hd.n_local = h->n_local; hd.n_neuron = h->N;
+    for (u64 v : h->n_local_all) hd.n_syn_global += v;
+    hd.rank = h->p.rank; hd.world = h->p.world_size; hd.n_output = h->p.n_output; hd.fir_size = h->p.fir_size;
+    hd.grow_count = h->d.grow ? std::min(sc.grow_count, h->grow_cap) : 0;
+    hd.snapshot = h->d.view != h->d.live;
+    std::vector<char> buf(64u << 20);
+    int rc = 0;
+    bool ok = put(f, &hd, sizeof hd) && put(f, &h->p, sizeof h->p) && put(f, &sc, sizeof sc) &&
+              put(f, h->n_local_all.data(), h->n_local_all.size() * sizeof(u64));
+    if (!ok) rc = fail(ABNN_ERR_IO, "short write");
+    const size_t no = h->p.n_output;
+    if (!rc) rc = dev_to_file(h, f, h->rs.rate, no * sizeof(float), buf);
+    if (!rc) rc = dev_to_file(h, f, h->rs.iir, no * sizeof(float), buf);
+    if (!rc) rc = dev_to_file(h, f, h->rs.fir, (size_t)h->p.fir_size * no * sizeof(float), buf);
+    if (!rc) rc = dev_to_file(h, f, h->rs.smooth, no * sizeof(float), buf);
+    if (!rc) rc = dev_to_file(h, f, h->d.live, h->N * sizeof(u64), buf);
+    if (!rc) rc = dev_to_file(h, f, h->d.visited, h->N * sizeof(u64), buf);
+    if (!rc && hd.snapshot) rc = dev_to_file(h, f, h->d.view, h->N * sizeof(u64), buf);
+    if (!rc && hd.grow_count) rc = dev_to_file(h, f, h->d.grow, (size_t)hd.grow_count * sizeof(GrowCand), buf);
+    if (!rc) rc = dev_to_file(h, f, h->d_syn, h->n_local * sizeof(abnn_synapse), buf);
+    if (std::fclose(f) != 0 && !rc) rc = fail(ABNN_ERR_IO, std::string("short write: ") + path);
+    return rc;
+}
+
+int abnn_load_state(abnn_handle* h, const char* path)
+{
+    RET(use(h));
+    if (!path) return fail(ABNN_ERR_INVALID, "null path");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(ABNN_ERR_IO, std::string("cannot open: ") + path);
+    Bnn2Header hd{};
+    abnn_params saved{};
+    DevScalars sc{};
+    int rc = 0;
+    if (!get(f, &hd, sizeof hd) || std::memcmp(hd.magic, "BNN2", 4) != 0 || hd.version != 2) rc = fail(ABNN_ERR_IO, "not a .bnn v2 file");
+    else if (hd.scalars_size != sizeof(DevScalars) || hd.params_size != sizeof(abnn_params)) rc = fail(ABNN_ERR_SHAPE, ".bnn v2 written by a different library build");
+    else if (hd.n_neuron != h->N || hd.rank != h->p.rank || hd.world != h->p.world_size || hd.n_output != h->p.n_output ||
+             hd.fir_size != h->p.fir_size || hd.snapshot != (u32)(h->d.view != h->d.live))
+        rc = fail(ABNN_ERR_SHAPE, ".bnn v2 header does not match the handle (neurons / rank / world / read-out / src view)");
+    else if (hd.n_local > h->cap) rc = fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded");
+    else if (hd.grow_count && (!h->d.grow || hd.grow_count > h->grow_buf)) rc = fail(ABNN_ERR_SHAPE, ".bnn v2 holds staged growth but the handle has p_new = 0");
+    std::vector<u64> counts(h->p.world_size);
+    if (!rc && !(get(f, &saved, sizeof saved) && get(f, &sc, sizeof sc) && get(f, counts.data(), counts.size() * sizeof(u64))))
+        rc = fail(ABNN_ERR_IO, "short read");
+    std::vector<char> buf(64u << 20);
+    const size_t no = h->p.n_output;
+    if (!rc) rc = file_to_dev(h, f, h->rs.rate, no * sizeof(float), buf);
+    if (!rc) rc = file_to_dev(h, f, h->rs.iir, no * sizeof(float), buf);
+    if (!rc) rc = file_to_dev(h, f, h->rs.fir, (size_t)h->p.fir_size * no * sizeof(float), buf);
+    if (!rc) rc = file_to_dev(h, f, h->rs.smooth, no * sizeof(float), buf);
+    if (!rc) rc = file_to_dev(h, f, h->d.live, h->N * sizeof(u64), buf);
+    if (!rc) rc = file_to_dev(h, f, h->d.visited, h->N * sizeof(u64), buf);
+    if (!rc && hd.snapshot) rc = file_to_dev(h, f, h->d.view, h->N * sizeof(u64), buf);
+    if (!rc && hd.grow_count) rc = file_to_dev(h, f, h->d.grow, (size_t)hd.grow_count * sizeof(GrowCand), buf);
+    if (!rc) rc = file_to_dev(h, f, h->d_syn, hd.n_local * sizeof(abnn_synapse), buf);
+    std::fclose(f);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(h->d.sc, &sc, sizeof sc, cudaMemcpyHostToDevice, h->st) != cudaSuccess || cudaStreamSynchronize(h->st) != cudaSuccess)
+        return fail(ABNN_ERR_CUDA, "device write failed during load");
+    h->n_local = hd.n_local; h->n_local_all = counts; h->counts_dirty = false;
+    return 0;
+}
+
+// ---- manifest (host only) --------------------------------------------------------------------------
+namespace {
+enum FieldType { F_U32, F_U64, F_F32, F_F64, F_I32 };
+struct Field { const char* name; FieldType type; size_t off; };
+#define FLD(n, t) {#n, t, offsetof(abnn_params, n)}
+const Field kFields[] = {
+    FLD(n_input, F_U32), FLD(n_output, F_U32), FLD(n_hidden, F_U64), FLD(n_syn, F_U64), FLD(syn_capacity, F_U64), FLD(seed, F_U64),
+    FLD(sampler, F_U32), FLD(release_rng, F_U32), FLD(clock_mode, F_U32), FLD(exec_mode, F_U32), FLD(src_view, F_U32),
+    FLD(rbar_mode, F_U32), FLD(max_spikes_per_pass, F_U32), FLD(track_visits, F_U32), FLD(window_pre, F_U64),
+    FLD(refractory, F_U64), FLD(teacher_gap, F_U64), FLD(base_scale, F_F32), FLD(a_ltp, F_F32), FLD(a_ltd, F_F32),
+    FLD(w_min, F_F32), FLD(w_max, F_F32), FLD(eta_home, F_F32), FLD(target_rate_hz, F_F32), FLD(home_tick_hz, F_F32),
+    FLD(eta_reward, F_F32), FLD(alpha_rbar, F_F32), FLD(w_prune, F_F32), FLD(p_new, F_F32), FLD(w_init, F_F32),
+    FLD(rate_alpha, F_F32), FLD(peak_decay, F_F32), FLD(peak_init, F_F32), FLD(use_fir, F_U32), FLD(fir_size, F_U32),
+    FLD(reward_window, F_U32), FLD(filter_tau, F_F64), FLD(dt_sec, F_F64), FLD(loss0, F_F64), FLD(device, F_I32),
+    FLD(l2_persist, F_U32), FLD(sample_block, F_U32), FLD(table_order, F_U32),
+};
+#undef FLD
+std::string trim(const std::string& s)
+{
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) ++a;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+bool parse_number(std::string v, double* out, u64* out_u, bool* is_int)
+{
+    if (v.size() >= 2 && (v.front() == '"' || v.front() == '\'') && v.back() == v.front()) v = v.substr(1, v.size() - 2);
+    std::string t;
+    for (char c : v) if (c != '_') t.push_back(c);
+    if (t.empty()) return false;
+    char* end = nullptr;
+    errno = 0;
+    const unsigned long long u = std::strtoull(t.c_str(), &end, 10);
+    if (errno == 0 && end && *end == 0 && t[0] != '-') { *out_u = u; *out = (double)u; *is_int = true; return true; }
+    end = nullptr;
+    const double d = std::strtod(t.c_str(), &end);
+    if (!end || *end != 0) return false;
+    *out = d; *out_u = d < 0 ? 0 : (u64)d; *is_int = false;
+    return true;
+}
+}  // namespace
+
+int abnn_params_from_manifest(const char* path, abnn_params* p, uint64_t* steps_out, uint64_t* tau_ltd_out)
+{
+    if (!path || !p) return fail(ABNN_ERR_INVALID, "null argument");
+    if (p->struct_size != sizeof(abnn_params)) return fail(ABNN_ERR_INVALID, "abnn_params must hold defaults (abnn_default_params) before a manifest is applied");
+    FILE* f = std::fopen(path, "r");
+    if (!f) return fail(ABNN_ERR_IO, std::string("cannot open: ") + path);
+    char line[4096];
+    bool have_neurons = false;
+    u64 neurons = 0;
+    int lineno = 0;
+    while (std::fgets(line, sizeof line, f)) {
+        ++lineno;
+        std::string s(line);
+        if (s.empty() || std::isspace((unsigned char)s[0]) || s[0] == '#' || s[0] == '-') continue;   // nested block / list / comment
+        const size_t hash = s.find('#');
+        if (hash != std::string::npos) s = s.substr(0, hash);
+        const size_t colon = s.find(':');
+        if (colon == std::string::npos) continue;
+        const std::string key = trim(s.substr(0, colon)), val = trim(s.substr(colon + 1));
+        if (val.empty()) continue;                         // start of a nested block
+        double d = 0; u64 u = 0; bool is_int = false;
+        const bool num = parse_number(val, &d, &u, &is_int);
+        auto need_num = [&]() -> int {
+            if (num) return 0;
+            std::fclose(f);
+            return fail(ABNN_ERR_INVALID, std::string(path) + ":" + std::to_string(lineno) + ": `" + key + "` needs a number, got `" + val + "`");
+        };
+        if (key == "neurons")        { RET(need_num()); neurons = u; have_neurons = true; }
+        else if (key == "synapses")  { RET(need_num()); p->n_syn = u; }
+        else if (key == "tau_LTP")   { RET(need_num()); p->window_pre = u; }
+        else if (key == "tau_LTD")   { RET(need_num()); if (tau_ltd_out) *tau_ltd_out = u; }
+        else if (key == "alpha_LTP") { RET(need_num()); p->a_ltp = (float)d; }
+        else if (key == "alpha_LTD") { RET(need_num()); p->a_ltd = (float)d; }
+        else if (key == "steps")     { RET(need_num()); if (steps_out) *steps_out = u; }
+        else if (key == "rng_seed")  { RET(need_num()); p->seed = u; }
+        else {
+            for (const Field& fd : kFields) {
+                if (key != fd.name) continue;
+                RET(need_num());
+                char* base = reinterpret_cast<char*>(p) + fd.off;
+                switch (fd.type) {
+                    case F_U32: *reinterpret_cast<uint32_t*>(base) = (uint32_t)u; break;
+                    case F_U64: *reinterpret_cast<uint64_t*>(base) = u; break;
+                    case F_I32: *reinterpret_cast<int32_t*>(base) = (int32_t)d; break;
+                    case F_F32: *reinterpret_cast<float*>(base) = (float)d; break;
+                    case F_F64: *reinterpret_cast<double*>(base) = d; break;
+                }
+                break;
+            }
+        }
+    }
+    std::fclose(f);
+    if (have_neurons) {
+        const u64 io = (u64)p->n_input + p->n_output;
+        if (neurons < io) return fail(ABNN_ERR_INVALID, "manifest: `neurons` is smaller than n_input + n_output");
+        p->n_hidden = neurons - io;
+    }
     return 0;
 }
 

@@ -226,6 +226,13 @@ int abnn_download_synapses(abnn_handle* h, abnn_synapse* out, uint64_t cap, uint
 int abnn_save_bnn(abnn_handle* h, const char* path);
 int abnn_load_bnn(abnn_handle* h, const char* path);             /* ABNN_ERR_SHAPE on mismatch (brain.cpp:174) */
 
+/* .bnn v2 (new; README.md:237-241 lists what v1 lacks): everything needed to resume EXACTLY where the run
+ * stopped — this rank's records, lastFired / lastVisited / snapshot, clock, pass and event counters,
+ * reward, r-bar, read-out filter state, staged growth candidates. Header "BNN2", shape-checked like v1.
+ * One file per rank. Both synchronise. */
+int abnn_save_state(abnn_handle* h, const char* path);
+int abnn_load_state(abnn_handle* h, const char* path);
+
 /* ---- per-pass operations ---------------------------------------------------------------- */
 /* Brain::inject_inputs (brain.cpp:73-83): input i spikes at `now` iff u < hz*kTickNS*NSEC_PER_SEC*v[i]. */
 int abnn_inject_inputs(abnn_handle* h, const float* v, uint32_t n, float hz);
@@ -263,6 +270,15 @@ int abnn_get_clock(abnn_handle* h, uint64_t* clock);
 int abnn_set_clock(abnn_handle* h, uint64_t clock);
 
 /* ---- host-only helpers (no device needed) -------------------------------------------------- */
+/* Flat-key YAML manifest -> abnn_params (abnn/manifests/simple.yml:3-12; the reference bundles the file but
+ * never parses these keys). *p must already hold defaults (abnn_default_params). Top-level `key: value`
+ * lines only; nested blocks, lists and unknown keys are skipped; numbers may carry `_` separators
+ * (`20_000` — a string under YAML 1.2, which is why the reference's own parser would not read it).
+ * Reference keys: neurons (total) -> n_hidden = neurons - n_input - n_output, synapses -> n_syn,
+ * tau_LTP -> window_pre, alpha_LTP -> a_ltp, alpha_LTD -> a_ltd, w_min, w_max, rng_seed -> seed;
+ * tau_LTD and steps are accepted and returned through the optional outputs (no kernel parameter uses
+ * them, in the reference or here). Any abnn_params field name is accepted as a key too. */
+int abnn_params_from_manifest(const char* path, abnn_params* p, uint64_t* steps_out, uint64_t* tau_ltd_out);
 /* Destination-neuron range of `rank`: [lo, hi), slices of ceil(n_neuron/world). */
 int abnn_partition(uint64_t n_neuron, uint32_t world_size, uint32_t rank, uint64_t* lo, uint64_t* hi);
 /* Events rank r executes in a pass of `events` when shard r holds n_local of n_global synapses and

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <functional>
@@ -183,6 +184,46 @@ private:
     std::function<float(float)> funcInput_, funcExpected_;
 };
 
+// Logger (abnn/src/core/singletons/logger.{h,cpp}): Octave/MATLAB animation script of input vs filtered
+// output (one frame per log_samples call) and the loss EMA (beta = 0.98), truncated every 10 losses.
+class Logger {
+public:
+    Logger(int nInput, int nOutput, const std::string& file = "abnn_session.m") : nIn_(nInput), nOut_(nOutput), file_(file) { open(); }
+    void log_samples(const std::vector<float>& in, const std::vector<float>& out)          // logger.cpp:25-56
+    {
+        if (!mat_) return;
+        mat_ << "clf;\nhold on;\nylim([-1 1]);\n";
+        mat_ << "xo = [ "; for (int i = 0; i < nOut_; ++i) mat_ << i << " "; mat_ << "];\n";
+        mat_ << "x = [ ";  for (size_t i = 0; i < in.size(); ++i) mat_ << i << " "; mat_ << "];\n";
+        mat_ << "y = [ ";  for (size_t i = 0; i < in.size(); ++i) mat_ << in[i] << " "; mat_ << "];\n";
+        mat_ << "\nz=[";   for (size_t i = 0; i < out.size(); ++i) { if (i) mat_ << ","; mat_ << out[i]; }
+        mat_ << "];title('Output');\n";
+        mat_ << "scatter(x,y,[],[],[0,0,1]);\nscatter(xo,z,[],[],[0,1,0]);\nhold off; pause(0.03);\n\n";
+        mat_.flush();
+        ++frames_;
+    }
+    void accumulate_loss(double loss)                                                       // logger.cpp:59-69
+    {
+        ema_ = step_ == 0 ? loss : beta_ * ema_ + (1.0 - beta_) * loss;
+        ++step_;
+        if (verbose) std::printf("EMA-Loss: %g  Raw loss: %g\n", ema_, loss);
+        if (step_ % 10 == 0) flush();
+    }
+    void flush() { mat_.flush(); mat_.close(); open(); }                                   // logger.cpp:71-84
+    double ema() const { return ema_; }
+    uint64_t losses() const { return step_; }
+    uint64_t frames() const { return frames_; }
+    bool verbose = false;
+
+private:
+    void open() { mat_.open(file_, std::ios::trunc); if (mat_) mat_ << "% ABNN animated session\n"; }
+    int nIn_, nOut_;
+    std::string file_;
+    std::ofstream mat_;
+    double ema_ = 0.0, beta_ = 0.98;
+    uint64_t step_ = 0, frames_ = 0;
+};
+
 class BrainEngine {                                     // brain-engine.h:33-85
 public:
     BrainEngine(uint32_t nInput, uint32_t nOutput, uint64_t eventsPerPass = EVENTS_PER_PASS,
@@ -193,6 +234,7 @@ public:
         brain_ = std::make_unique<Brain>(nIn_, nOut_, p.n_hidden, p.n_syn, eventsPerPass_, &p);   // brain-engine.cpp:66
         brain_->build_pipeline();
         brain_->build_buffers();
+        rewardWindow_ = p.reward_window;
         if (!load_model()) {                            // brain-engine.cpp:72-75
             brain_->build_random_graph(1);
             save_model();
@@ -243,15 +285,29 @@ public:
         even_ = !even_;
         brain_->encode_traversal();                                                       // :136-141
         ++step_;
-        return brain_->readout_filtered(&expected);                                       // :143-186 (synchronises)
+        std::vector<float> smooth = brain_->readout_filtered(&expected);                  // :143-186 (synchronises)
+        if (logger_) {
+            if (step_ % 100 == 0) logger_->log_samples(in, smooth);                       // :166-168
+            if (rewardWindow_ && step_ % rewardWindow_ == 0) {                            // :173-186 (loss computed on the device)
+                double loss = 0.0; uint64_t windows = 0;
+                check(abnn_get_loss(brain_->handle(), &loss, &windows), "abnn_get_loss");
+                logger_->accumulate_loss(loss);
+            }
+        }
+        return smooth;
     }
+    // Attach the reference's Logger (writes abnn_session.m in the working directory by default).
+    void enable_logger(const std::string& file = "abnn_session.m") { logger_ = std::make_unique<Logger>((int)nIn_, (int)nOut_, file); }
+    Logger* logger() { return logger_.get(); }
 
     Brain& brain() { return *brain_; }
     uint64_t step() const { return step_; }
 
 private:
     std::unique_ptr<Brain> brain_;
+    std::unique_ptr<Logger> logger_;
     std::shared_ptr<StimulusProvider> stim_;
+    uint32_t rewardWindow_ = 0;
     std::thread worker_;
     std::atomic<bool> running_{false};
     uint32_t nIn_, nOut_;

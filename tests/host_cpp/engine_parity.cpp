@@ -27,6 +27,7 @@ int main(int argc, char** argv)
                                                         [](float x) { return cos(x) * cos(x); },           // view-delegate.cpp:37-39
                                                         [](float x) { return 0.5f * sin(x) + 0.5f; });     // view-delegate.cpp:40-42
         engine.set_stimulus(stim);
+        engine.enable_logger(std::string(argv[1]) + ".session.m");
         std::ofstream out(argv[1], std::ios::binary);
         for (int i = 0; i < passes; ++i) {
             const std::vector<float> r = engine.run_one_pass();
@@ -52,8 +53,9 @@ int main(int argc, char** argv)
         engine.start_async();
         while (engine.step() < before + 3) std::this_thread::yield();
         engine.stop_async();
-        std::printf("ok passes=%d async_passes=%llu clock=%llu\n", passes, (unsigned long long)(engine.step() - before),
-                    (unsigned long long)engine.brain().clock());
+        std::printf("ok passes=%d async_passes=%llu clock=%llu logger_losses=%llu ema=%.9g\n", passes,
+                    (unsigned long long)(engine.step() - before), (unsigned long long)engine.brain().clock(),
+                    (unsigned long long)engine.logger()->losses(), engine.logger()->ema());
     } catch (const std::exception& e) {
         std::fprintf(stderr, "engine_parity: %s\n", e.what());
         return 1;

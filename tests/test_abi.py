@@ -101,3 +101,26 @@ def test_create_without_a_gpu_fails_loudly():
     assert b"no CPU fallback" in lib.abnn_last_error()
     import torch                                         # loading the library first must not break PyTorch's NCCL
     assert not torch.cuda.is_available()
+
+
+def test_manifest_loader(tmp_path):
+    """abnn_params_from_manifest on the reference's flat keys (simple.yml:3-12): underscore numbers,
+    comments, nested blocks skipped, reference key names mapped, abnn_params field names accepted."""
+    lib = capi.load()
+    p = capi.default_params(capi.PROFILE_NORTH_STAR)
+    steps, tau_ltd = C.c_uint64(), C.c_uint64()
+    path = os.path.join(ROOT, "tests", "golden", "abnn_manifest.yml").encode()
+    assert lib.abnn_params_from_manifest(path, C.byref(p), C.byref(steps), C.byref(tau_ltd)) == 0, lib.abnn_last_error()
+    assert (p.n_input, p.n_output, p.n_hidden, p.n_syn) == (256, 256, 65536 - 512, 524288)
+    assert (p.window_pre, tau_ltd.value, steps.value, p.seed) == (20_000, 40_000, 1_000_000, 42)
+    assert (np.float32(p.a_ltp), np.float32(p.a_ltd)) == (np.float32(0.01), np.float32(0.005))
+    assert (np.float32(p.w_min), np.float32(p.w_max)) == (np.float32(0.001), np.float32(1.0))      # nested w_max ignored
+    assert (p.sample_block, p.table_order) == (8, capi.TABLE_DST_SORTED)
+    bad = tmp_path / "bad.yml"
+    bad.write_text("synapses: lots\n")
+    assert lib.abnn_params_from_manifest(str(bad).encode(), C.byref(p), None, None) == capi.ERR_INVALID
+    assert b"needs a number" in lib.abnn_last_error()
+    small = tmp_path / "small.yml"
+    small.write_text("neurons: 100\n")
+    assert lib.abnn_params_from_manifest(str(small).encode(), C.byref(p), None, None) == capi.ERR_INVALID
+    assert lib.abnn_params_from_manifest(b"/nonexistent.yml", C.byref(p), None, None) == capi.ERR_IO

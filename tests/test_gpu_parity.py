@@ -362,6 +362,46 @@ def test_bnn_roundtrip_and_shape_error(tmp_path):
         assert e.value.status == capi.ERR_SHAPE                                                  # brain.cpp:174
 
 
+def test_bnn_v2_exact_resume(tmp_path):
+    """.bnn v2: stop after 3 passes, reload into a fresh handle, continue — the continuation equals the
+    uninterrupted run (and the oracle) bit for bit, including read-out filter state, reward window and
+    staged growth candidates."""
+    over = dict(n_input=64, n_output=64, n_hidden=3000, n_syn=120_000, exec_mode=capi.EXEC_EXACT, sample_block=8,
+                table_order=capi.TABLE_DST_SORTED, window_pre=400_000, refractory=20_000, p_new=0.05, reward_window=4,
+                syn_capacity=130_000)
+    path = str(tmp_path / "state.bnn2")
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.build_random_graph(1); o.init_graph(capi.GRAPH_REFERENCE, 1)
+    stim_b, stim_o = FunctionalDataset(64, 64), FunctionalDataset(64, 64)
+
+    def step(x, stim, p):
+        vin, exp = stim.nextInput(), stim.nextExpected()
+        x.inject_inputs(vin, 1000.0); x.teacher_force(exp, float(p & 1))
+        st = x.run_pass(100_000)
+        return st, x.readout_filtered(exp)
+
+    for p in range(3):
+        sb, rb = step(b, stim_b, p); so, ro = step(o, stim_o, p)
+        assert_same_stats(sb, so, f"pass {p}") ; assert rb.tobytes() == ro.tobytes()
+    b.save_state(path)
+    b.close()
+    b2 = Brain(O.default_params(capi.PROFILE_NORTH_STAR, **over))
+    b2.load_state(path)
+    for p in range(3, 7):
+        sb, rb = step(b2, stim_b, p); so, ro = step(o, stim_o, p)
+        assert_same_stats(sb, so, f"resumed pass {p}"); assert rb.tobytes() == ro.tobytes()
+        if p == 4:
+            ssb, sso = b2.prune_and_grow(), o.prune_and_grow()
+            assert (ssb.appended, ssb.n_after) == (sso.appended, sso.n_after) and sso.appended > 0
+    assert_same_state(b2, o, "after resume")
+    assert b2.get_loss() == o.get_loss() and o.get_loss()[1] == 1
+    q = O.default_params(capi.PROFILE_NORTH_STAR, **dict(over, n_hidden=3001))
+    with Brain(q) as other:
+        with pytest.raises(capi.AbnnError) as e:
+            other.load_state(path)
+        assert e.value.status == capi.ERR_SHAPE
+
+
 # ---- structural plasticity ---------------------------------------------------------------------------
 def test_prune_compaction_is_stable_and_matches_oracle():
     rng = np.random.default_rng(3)
