@@ -184,6 +184,13 @@ class Brain:
         lv = None if lv is None else np.ascontiguousarray(lv, dtype=np.uint64)
         capi.check(self.lib.abnn_upload_timestamps(self.h, _ptr(lf), _ptr(lv)), "abnn_upload_timestamps")
 
+    def gate_words(self):
+        """(words, valid): the 32-bit pre-spike gate words prepared for the next pass (inspection)."""
+        w = np.zeros(self._n_neuron, np.uint32)
+        v = C.c_uint32()
+        capi.check(self.lib.abnn_download_gate_words(self.h, _ptr(w), C.byref(v)), "abnn_download_gate_words")
+        return w, bool(v.value)
+
     @property
     def clock(self) -> int:
         c = C.c_uint64()

@@ -126,6 +126,7 @@ SIGNATURES = {
     "abnn_prune_and_grow": (C.c_int, [_H, _P(StructuralStats)]),
     "abnn_download_timestamps": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "abnn_upload_timestamps": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "abnn_download_gate_words": (C.c_int, [_H, C.c_void_p, _P(C.c_uint32)]),
     "abnn_get_clock": (C.c_int, [_H, _P(C.c_uint64)]),
     "abnn_set_clock": (C.c_int, [_H, C.c_uint64]),
     "abnn_partition": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64)]),

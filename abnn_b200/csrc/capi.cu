@@ -91,6 +91,9 @@ struct abnn_handle {
     u64* d_xkeys = nullptr; u64* d_xvals = nullptr; u32* d_xcount = nullptr; void* d_xtmp = nullptr;
     u64 x_cap = 0; size_t x_tmp_bytes = 0;
     bool timing = false;
+    // sharded PARALLEL runs exchange the 32-bit slack slices instead of the 64-bit lastFired slices:
+    bool slack_ready = false;             // d.slack already holds the next pass's gate words (all but the in/out head)
+    bool view_stale = false;              // remote slices of d.view were not refreshed by the last exchange
 };
 
 namespace {
@@ -192,13 +195,49 @@ int read_scalars(abnn_handle* h, DevScalars* out)
     return 0;
 }
 
+// The line kernel gates on the 32-bit slack words (traversal.cu:k_build_slack) when it can.
+bool slack_mode(const abnn_handle* h, const KParams& kp)
+{
+    static const bool off = getenv("ABNN_NO_SLACK") != nullptr;
+    return h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && line_kernel_selected(kp) && kp.ticks < 0xFFFFFFF0ull && !off;
+}
+
+// Bring every rank's lastFired slice into the replicated 64-bit snapshot (collective when world_size > 1).
+int ensure_view(abnn_handle* h)
+{
+    if (!h->view_stale) return 0;
+    if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
+    NC(ncclAllGather(h->d.live + h->lo, h->d.view, h->slice, ncclUint64, h->comm, h->st));
+    h->view_stale = false;
+    return 0;
+}
+
 // After the events of a pass: every rank's owned lastFired slice becomes visible to everyone
 // (per-pass allgather of fired-neuron timestamps over NVLink).
-int exchange_timestamps(abnn_handle* h)
+// Sharded PARALLEL runs on the line kernel need the remote timestamps only as gate words of the NEXT
+// pass, so each rank turns its own slice into slack words (the clock has already been advanced by
+// k_end_pass) and the ranks allgather those — half the bytes — plus a broadcast of the input/output
+// head of lastFired that teacher forcing and the read-out look at. The 64-bit snapshot of the remote
+// slices is refreshed lazily (ensure_view) when something asks for it.
+int exchange_timestamps(abnn_handle* h, const KParams& kp)
 {
+    static const bool full = getenv("ABNN_FULL_EXCHANGE") != nullptr;       // measurements only
+    const u64 head = (u64)h->p.n_input + h->p.n_output;
+    h->slack_ready = false;
     if (h->p.world_size > 1) {
         if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
-        NC(ncclAllGather(h->d.live + h->lo, h->d.view, h->slice, ncclUint64, h->comm, h->st));
+        if (slack_mode(h, kp) && h->slice >= head && !full) {
+            CU(launch_build_slack(kp, h->d, h->d.live, h->lo, h->hi, h->st));
+            NC(ncclGroupStart());
+            NC(ncclAllGather(h->d.slack + h->lo, h->d.slack, h->slice, ncclUint32, h->comm, h->st));
+            NC(ncclBroadcast(h->d.live, h->d.view, head, ncclUint64, 0, h->comm, h->st));
+            NC(ncclGroupEnd());
+            h->slack_ready = true;
+            h->view_stale = true;
+        } else {
+            NC(ncclAllGather(h->d.live + h->lo, h->d.view, h->slice, ncclUint64, h->comm, h->st));
+            h->view_stale = false;
+        }
     } else if (h->d.view != h->d.live) {
         CU(cudaMemcpyAsync(h->d.view, h->d.live, h->N * sizeof(u64), cudaMemcpyDeviceToDevice, h->st));
     }
@@ -738,6 +777,7 @@ int abnn_save_state(abnn_handle* h, const char* path)
     RET(use(h));
     if (!path) return fail(ABNN_ERR_INVALID, "null path");
     RET(refresh_counts(h));
+    RET(ensure_view(h));
     DevScalars sc; RET(read_scalars(h, &sc));
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(ABNN_ERR_IO, std::string("cannot open for writing: ") + path);
@@ -804,6 +844,7 @@ int abnn_load_state(abnn_handle* h, const char* path)
     if (cudaMemcpyAsync(h->d.sc, &sc, sizeof sc, cudaMemcpyHostToDevice, h->st) != cudaSuccess || cudaStreamSynchronize(h->st) != cudaSuccess)
         return fail(ABNN_ERR_CUDA, "device write failed during load");
     h->n_local = hd.n_local; h->n_local_all = counts; h->counts_dirty = false;
+    h->slack_ready = false; h->view_stale = false;
     return 0;
 }
 
@@ -955,11 +996,15 @@ int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
     RET(refresh_counts(h));
     KParams kp = make_kparams(h, events);
     if (stats) CU(cudaEventRecord(h->ev0, h->st));
-    if (h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && line_kernel_selected(kp) && kp.ticks < 0xFFFFFFF0ull &&
-        !getenv("ABNN_NO_SLACK")) {
+    if (slack_mode(h, kp)) {
         kp.use_slack = 1;
-        CU(launch_build_slack(kp, h->d, h->st));
-    }
+        if (h->slack_ready) {           // the exchange delivered the gate words; inject / teacher forcing touched the head since
+            CU(launch_build_slack(kp, h->d, h->d.view, 0, (u64)h->p.n_input + h->p.n_output, h->st));
+        } else {
+            RET(ensure_view(h));
+            CU(launch_build_slack(kp, h->d, h->d.view, 0, h->N, h->st));
+        }
+    } else RET(ensure_view(h));
     switch (h->p.exec_mode) {
         case ABNN_EXEC_SERIAL:   CU(launch_traverse_serial(kp, h->d, h->st)); break;
         case ABNN_EXEC_PARALLEL: CU(launch_traverse_parallel(kp, h->d, h->sm_count, h->st)); break;
@@ -967,7 +1012,7 @@ int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
     }
     if (stats) CU(cudaEventRecord(h->evk, h->st));
     CU(launch_end_pass(kp, h->d.sc, h->d_stats, h->st));
-    RET(exchange_timestamps(h));
+    RET(exchange_timestamps(h, kp));
     if (stats) {
         CU(cudaEventRecord(h->ev1, h->st));
         CU(cudaMemcpyAsync(h->h_pin, h->d_stats, sizeof(abnn_pass_stats), cudaMemcpyDeviceToHost, h->st));
@@ -1140,6 +1185,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
 int abnn_download_timestamps(abnn_handle* h, uint64_t* lf, uint64_t* lv)
 {
     RET(use(h));
+    RET(ensure_view(h));                 // collective when world_size > 1: every rank downloads together
     // lastFired: the replicated view is what every rank agrees on after a pass; single GPU: live.
     const u64* src = h->p.world_size > 1 ? h->d.view : h->d.live;
     if (lf) CU(cudaMemcpyAsync(lf, src, h->N * sizeof(u64), cudaMemcpyDeviceToHost, h->st));
@@ -1150,11 +1196,22 @@ int abnn_download_timestamps(abnn_handle* h, uint64_t* lf, uint64_t* lv)
 int abnn_upload_timestamps(abnn_handle* h, const uint64_t* lf, const uint64_t* lv)
 {
     RET(use(h));
+    h->slack_ready = false;
+    if (lf) h->view_stale = false;
     if (lf) {
         CU(cudaMemcpyAsync(h->d.live, lf, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
         if (h->d.view != h->d.live) CU(cudaMemcpyAsync(h->d.view, lf, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
     }
     if (lv) CU(cudaMemcpyAsync(h->d.visited, lv, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int abnn_download_gate_words(abnn_handle* h, uint32_t* words, uint32_t* valid_out)
+{
+    RET(use(h));
+    if (valid_out) *valid_out = h->slack_ready ? 1u : 0u;
+    if (!h->d.slack || !words) return h->d.slack || !words ? 0 : fail(ABNN_ERR_UNSUPPORTED, "this handle has no gate words (LIVE src view)");
+    CU(cudaMemcpyAsync(words, h->d.slack, h->N * sizeof(u32), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -1169,6 +1226,7 @@ int abnn_get_clock(abnn_handle* h, uint64_t* clock)
 int abnn_set_clock(abnn_handle* h, uint64_t clock)
 {
     RET(use(h));
+    h->slack_ready = false;             // the gate words are relative to the clock
     k_set_clock<<<1, 1, 0, h->st>>>(h->d.sc, clock);
     CU(cudaGetLastError());
     return 0;

@@ -7,8 +7,8 @@ namespace abnn {
 // traversal.cu
 cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st);
 cudaError_t launch_traverse_serial(const KParams& kp, const DevPtrs& d, cudaStream_t st);
-// slack[n] for the pass that starts at sc->clock and spans kp.ticks ticks (see k_build_slack)
-cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, cudaStream_t st);
+// slack[n], n in [n0, n1), from lastFired values src[n] for the pass that starts at sc->clock (see k_build_slack)
+cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* src, u64 n0, u64 n1, cudaStream_t st);
 bool line_kernel_selected(const KParams& kp);
 cudaError_t launch_end_pass(const KParams& kp, DevScalars* sc, abnn_pass_stats* out, cudaStream_t st);
 

@@ -396,11 +396,11 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
 // 0xFFFFFFFF marks the (pathological) neurons whose snapshot lies in the future of the pass start;
 // for those the kernel falls back to the exact 64-bit test.
 constexpr u32 SLACK_EXACT = 0xFFFFFFFFu;
-__global__ void __launch_bounds__(256) k_build_slack(const __grid_constant__ KParams kp, const DevPtrs d)
+__global__ void __launch_bounds__(256) k_build_slack(const __grid_constant__ KParams kp, const DevPtrs d, const u64* src, u64 n0, u64 n1)
 {
     const u64 clock = d.sc->clock;
-    for (u64 n = (u64)blockIdx.x * blockDim.x + threadIdx.x; n < kp.n_neuron; n += (u64)gridDim.x * blockDim.x) {
-        const u64 lp = d.view[n];
+    for (u64 n = n0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (u64)gridDim.x * blockDim.x) {
+        const u64 lp = src[n];
         u32 v;
         if (lp > clock) v = SLACK_EXACT;
         else {
@@ -411,12 +411,12 @@ __global__ void __launch_bounds__(256) k_build_slack(const __grid_constant__ KPa
         d.slack[n] = v;
     }
 }
-cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, cudaStream_t st)
+cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* src, u64 n0, u64 n1, cudaStream_t st)
 {
-    u64 blocks = (kp.n_neuron + 255) / 256;
+    if (n1 <= n0) return cudaSuccess;
+    u64 blocks = (n1 - n0 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (!blocks) return cudaSuccess;
-    k_build_slack<<<(unsigned)blocks, 256, 0, st>>>(kp, d);
+    k_build_slack<<<(unsigned)blocks, 256, 0, st>>>(kp, d, src, n0, n1);
     return cudaGetLastError();
 }
 

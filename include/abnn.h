@@ -266,6 +266,11 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* stats);   /* sync
 /* ---- raw state access: last_fired_buffer()/clock_buffer() (brain.h:54-58). All synchronise. - */
 int abnn_download_timestamps(abnn_handle* h, uint64_t* last_fired, uint64_t* last_visited); /* n_neuron each; NULL to skip */
 int abnn_upload_timestamps(abnn_handle* h, const uint64_t* last_fired, const uint64_t* last_visited);
+/* Inspection: the 32-bit pre-spike gate words the line kernel will read in the NEXT pass (n_neuron values;
+ * word = clamp(window_pre - (clock - lastFired_snapshot) + 1, 0, 2^32-2), traversal.cu:k_build_slack).
+ * *valid_out = 0 when they have not been prepared yet (they are rebuilt at the start of the pass: first
+ * pass, after abnn_set_clock / abnn_upload_timestamps, single-GPU handles, non-PARALLEL modes). Synchronises. */
+int abnn_download_gate_words(abnn_handle* h, uint32_t* words, uint32_t* valid_out);
 int abnn_get_clock(abnn_handle* h, uint64_t* clock);
 int abnn_set_clock(abnn_handle* h, uint64_t clock);
 

@@ -59,6 +59,62 @@ def _gpu_worker(rank, world, port, exec_mode, q, refractory=None):
         dist.destroy_process_group()
 
 
+def _gate_worker(rank, world, port, q):
+    """PARALLEL line kernel on a dst-sorted table, sharded: after every pass the exchanged 32-bit gate words
+    must equal clamp(window_pre - (clock - lastFired) + 1) of the replicated lastFired on every rank."""
+    import torch
+    import torch.distributed as dist
+    from abnn_b200 import distributed as D
+    from oracle import pyoracle as O
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        scen = dict(SCEN, refractory=3_000, p_new=0.0, w_prune=0.0, table_order=capi.TABLE_DST_SORTED)
+        base = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_PARALLEL, **scen)
+        b = D.create_sharded_brain(base, device=rank)
+        N, syn, pre, frames = _inputs()
+        b.upload_synapses(syn)
+        b.upload_timestamps(pre, None); b.clock = 500_000; b.set_reward(0.2)
+        out = []
+        for it, (vin, exp) in enumerate(frames):
+            b.inject_inputs(vin, 1000.0); b.teacher_force(exp, float(it & 1))
+            st = b.run_pass(300_000)
+            words, valid = b.gate_words()
+            lf, lv = b.timestamps()                       # collective: refreshes the 64-bit snapshot
+            out.append((st.events, st.fired, valid, words.tobytes(), lf.tobytes(), b.clock, b.read_outputs().tobytes()))
+        q.put((rank, out))
+        b.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_parallel_gate_word_exchange():
+    import multiprocessing as mp
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [ctx.Process(target=_gate_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    W = SCEN["window_pre"]
+    fired = 0
+    for it in range(4):
+        (ev0, f0, valid0, w0, lf0, c0, o0), (ev1, f1, valid1, w1, lf1, c1, o1) = res[0][it], res[1][it]
+        assert valid0 and valid1, "the sharded PARALLEL exchange must deliver the gate words"
+        assert w0 == w1 and lf0 == lf1 and c0 == c1 and o0 == o1, f"ranks disagree after pass {it}"
+        lf = np.frombuffer(lf0, np.uint64).astype(np.int64)
+        want = np.clip(W - (c0 - lf) + 1, 0, 0xFFFFFFFE).astype(np.uint32)
+        got = np.frombuffer(w0, np.uint32)
+        assert np.array_equal(got[32:], want[32:]), f"gate words differ from the lastFired snapshot after pass {it}"
+        fired += f0 + f1
+    assert fired > 1000
+
+
 def _run_gpu(exec_mode, refractory=None):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
