@@ -68,7 +68,7 @@ struct DevScalars {
     u32   fires_claimed;     // saturating budget (bufBudget_ counts down; this counts up)
     u32   grow_count;        // staged growth candidates since the last structural step
     u32   grow_overflow;
-    u32   pad0;
+    u32   chunk_ticket;      // next chunk of the pass to hand out (line kernel: dynamic work distribution)
     // read-out state (brain-engine.cpp:145-186; rate-filter.h)
     float max_observed;
     u32   iir_init;
