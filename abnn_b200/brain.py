@@ -136,6 +136,14 @@ class Brain:
         capi.check(self.lib.abnn_run_pass(self.h, events, C.byref(st)), "abnn_run_pass")
         return st
 
+    def engine_step(self, vin, expected, hz: float, teacher_rate: float, events: int, want_rates: bool = False):
+        """inject + teacher forcing + one pass + read-out step as one enqueue (CUDA graph replay in PARALLEL mode)."""
+        v = np.ascontiguousarray(vin, dtype=np.float32)
+        e = np.ascontiguousarray(expected, dtype=np.float32)
+        out = np.zeros(self.params.n_output, np.float32) if want_rates else None
+        capi.check(self.lib.abnn_engine_step(self.h, _ptr(v), _ptr(e), hz, teacher_rate, events, _ptr(out)), "abnn_engine_step")
+        return out
+
     def sync(self):
         capi.check(self.lib.abnn_sync(self.h), "abnn_sync")
 
@@ -250,12 +258,7 @@ class BrainEngine:
         b = self.brain
         vin = self.stim.nextInput()
         expected = self.stim.nextExpected()
-        b.inject_inputs(vin, INPUT_RATE_HZ)
-        b.teacher_force(expected, 1.0 if self._even else 0.0)
+        rate = 1.0 if self._even else 0.0
         self._even = not self._even
-        b.encode_traversal(self.events)
         self.step += 1
-        if want_rates:
-            return b.readout_filtered(expected)
-        b.readout_step(expected)
-        return None
+        return b.engine_step(vin, expected, INPUT_RATE_HZ, rate, self.events, want_rates)

@@ -117,6 +117,7 @@ SIGNATURES = {
     "abnn_get_reward": (C.c_int, [_H, _P(C.c_float), _P(C.c_float)]),
     "abnn_run_pass": (C.c_int, [_H, C.c_uint64, _P(PassStats)]),
     "abnn_sync": (C.c_int, [_H]),
+    "abnn_engine_step": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_uint64, C.c_void_p]),
     "abnn_timer_mark": (C.c_int, [_H, C.c_uint32]),
     "abnn_timer_elapsed": (C.c_int, [_H, C.c_uint32, C.c_uint32, _P(C.c_double)]),
     "abnn_read_outputs": (C.c_int, [_H, C.c_void_p, C.c_uint32]),

@@ -8,10 +8,14 @@
 namespace abnn {
 
 // Brain::inject_inputs (brain.cpp:73-83): lf[i] = now iff u < pTick * v[i].
-__global__ void k_inject(const __grid_constant__ KParams kp, const DevPtrs d, const float* __restrict__ v, u32 n, float pTick)
+// `scal` (nullable): the scalar argument read from device memory instead, so that a captured graph can be
+// replayed with a new value (abnn_engine_step).
+__global__ void k_inject(const __grid_constant__ KParams kp, const DevPtrs d, const float* __restrict__ v, u32 n, float pTick,
+                         const float* __restrict__ scal)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (scal) pTick = *scal;
     const u64 now = d.sc->clock, pass = d.sc->pass_index;
     const Philox4 r = philox4x32_10((u32)pass, (u32)(pass >> 32), i, STREAM_INJECT, kp.seed_lo, kp.seed_hi);
     if (u01_24(r.x) < pTick * v[i]) {
@@ -22,10 +26,11 @@ __global__ void k_inject(const __grid_constant__ KParams kp, const DevPtrs d, co
 
 // Teacher forcing (brain-engine.cpp:126-133).
 __global__ void k_teacher(const __grid_constant__ KParams kp, const DevPtrs d, const float* __restrict__ expected, u32 n,
-                          float rate, u64 gap)
+                          float rate, u64 gap, const float* __restrict__ scal)
 {
     const u32 o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n) return;
+    if (scal) rate = *scal;
     const u64 now = d.sc->clock, pass = d.sc->pass_index;
     const Philox4 r = philox4x32_10((u32)pass, (u32)(pass >> 32), o, STREAM_TEACHER, kp.seed_lo, kp.seed_hi);
     const float p = expected[o] * rate;
@@ -110,16 +115,17 @@ __global__ void __launch_bounds__(256) k_readout(const __grid_constant__ KParams
     }
 }
 
-cudaError_t launch_inject(const KParams& kp, const DevPtrs& d, const float* v, u32 n, float pTick, cudaStream_t st)
+cudaError_t launch_inject(const KParams& kp, const DevPtrs& d, const float* v, u32 n, float pTick, const float* scal, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_inject<<<(n + 255) / 256, 256, 0, st>>>(kp, d, v, n, pTick);
+    k_inject<<<(n + 255) / 256, 256, 0, st>>>(kp, d, v, n, pTick, scal);
     return cudaGetLastError();
 }
-cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* expected, u32 n, float rate, u64 gap, cudaStream_t st)
+cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* expected, u32 n, float rate, u64 gap, const float* scal,
+                           cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_teacher<<<(n + 255) / 256, 256, 0, st>>>(kp, d, expected, n, rate, gap);
+    k_teacher<<<(n + 255) / 256, 256, 0, st>>>(kp, d, expected, n, rate, gap, scal);
     return cudaGetLastError();
 }
 cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st)

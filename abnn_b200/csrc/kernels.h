@@ -27,8 +27,10 @@ struct ReadoutParams {
     double a;                       // dt / (tau + dt)   (rate-filter.h:29)
 };
 struct ReadoutState { float* rate; float* iir; float* fir; float* smooth; unsigned char* spikes; };
-cudaError_t launch_inject(const KParams& kp, const DevPtrs& d, const float* v, u32 n, float pTick, cudaStream_t st);
-cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* expected, u32 n, float rate, u64 gap, cudaStream_t st);
+// scal (nullable): read pTick / rate from device memory instead of the by-value argument (graph replay)
+cudaError_t launch_inject(const KParams& kp, const DevPtrs& d, const float* v, u32 n, float pTick, const float* scal, cudaStream_t st);
+cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* expected, u32 n, float rate, u64 gap, const float* scal,
+                           cudaStream_t st);
 cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st);
 cudaError_t launch_readout(const KParams& kp, const DevPtrs& d, const ReadoutParams& rp, const ReadoutState& rs,
                            const float* expected, cudaStream_t st);

@@ -260,10 +260,9 @@ def main():
             dist.barrier()
 
     def step_device(it):
-        b.inject_inputs(pin_in[it], 1000.0)
-        b.teacher_force(pin_ex[it], float(it & 1))
-        b.encode_traversal(args.events)
-        b.readout_step(pin_ex[it])
+        # BrainEngine::run_one_pass as one C-ABI call: stage frame, inject, teacher forcing, traversal, exchange,
+        # read-out step (replayed from a CUDA graph after the second call)
+        b.engine_step(pin_in[it], pin_ex[it], 1000.0, float(it & 1), args.events)
 
     # ---- value: device-timed, K steps ------------------------------------------------------------
     for it in range(W):
@@ -293,10 +292,7 @@ def main():
     t0 = time.perf_counter()
     for it in range(K):
         j = (W + K + 10 + it) % len(pin_in)
-        b.inject_inputs(pin_in[j], 1000.0)
-        b.teacher_force(pin_ex[j], float(it & 1))
-        b.encode_traversal(args.events)
-        b.readout_filtered(pin_ex[j])          # D2H + sync
+        b.engine_step(pin_in[j], pin_ex[j], 1000.0, float(it & 1), args.events, want_rates=True)   # H2D frame, D2H rates, sync
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -360,10 +356,10 @@ def main():
                          "kernel_ms": trav_mean, "alg_bytes_per_event": b_alg,
                          "sector_level_frac": ev_per_launch * (32.0 + 32.0 * g) / (trav_mean * 1e-3) / 1e9 / peak},
             "e2e": {"value": args.events * K / e2e_s, "unit": "events/s",
-                    "h2d_bytes_per_step": int(3 * N_IN * 4), "d2h_bytes_per_step": int(N_OUT * 4)},
-            # per step: k_inject, k_teacher, k_build_slack, traversal kernel, k_end_pass, k_readout (+ the snapshot copy /
-            # NCCL allgather, not counted)
-            "gpu_launches": 6 * K,
+                    "h2d_bytes_per_step": int((N_IN + N_OUT + 2) * 4), "d2h_bytes_per_step": int(N_OUT * 4)},
+            # per step (one CUDA-graph launch): k_inject, k_teacher, k_build_slack, traversal kernel, k_end_pass, k_readout
+            # (+ N>1: k_build_slack on the owned slice; the snapshot copy / NCCL kernels are not counted)
+            "gpu_launches": (6 if world == 1 else 7) * K,
             "clocks": clocks,
         }
         if world == 1 and not args.skip_cpu:

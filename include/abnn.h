@@ -246,6 +246,15 @@ int abnn_get_reward(abnn_handle* h, float* reward, float* rbar);         /* sync
  * `events` events. Asynchronous when stats == NULL; otherwise synchronises and fills *stats. */
 int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats);
 int abnn_sync(abnn_handle* h);                                           /* waitUntilCompleted */
+/* One whole engine pass without a host round trip — BrainEngine::run_one_pass (brain-engine.cpp:108-190):
+ * stage the stimulus frame, inject_inputs(in, hz), teacher forcing (expected, teacher_rate), `events`
+ * traversal events, timestamp exchange, read-out step with loss/reward. Equivalent to abnn_inject_inputs +
+ * abnn_teacher_force + abnn_run_pass(NULL) + abnn_readout_step; in PARALLEL execution on a single-GPU
+ * handle the device work is recorded into a CUDA graph on the second call and replayed while events /
+ * table size stay the same (sharded handles enqueue the same sequence eagerly).
+ * Asynchronous when rates == NULL; otherwise writes the n_output filtered rates and synchronises. */
+int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, float hz, float teacher_rate,
+                     uint64_t events, float* rates);
 /* Device-side stopwatch on the handle's stream (CUDA events; the stream is private to the handle, so
  * callers cannot time it with their own events): mark slot 0..7, then read the time between two marks.
  * abnn_timer_elapsed synchronises. */

@@ -86,6 +86,13 @@ public:
         check(abnn_readout_filtered(need(), expected ? expected->data() : nullptr, r.data(), p_.n_output), "abnn_readout_filtered");
         return r;
     }
+    // inject + teacher forcing + pass + read-out step in one enqueue (abnn_engine_step; CUDA-graph replay)
+    std::vector<float> engine_step(const std::vector<float>& in, const std::vector<float>& expected, float hz, float teacherRate)
+    {
+        std::vector<float> r(p_.n_output);
+        check(abnn_engine_step(need(), in.data(), expected.data(), hz, teacherRate, EVENTS_, r.data()), "abnn_engine_step");
+        return r;
+    }
     void set_reward(float r) { check(abnn_set_reward(need(), r), "abnn_set_reward"); }   // reward_buffer() poke, brain-engine.cpp:180-182
 
     /* graph */
@@ -280,12 +287,11 @@ public:
     {
         const std::vector<float> in = stim_->nextInput();                                 // :114
         const std::vector<float> expected = stim_->nextExpected();                        // :115
-        brain_->inject_inputs(in, INPUT_RATE_HZ);                                         // :117
-        brain_->teacher_force(expected, even_ ? 1.0f : 0.0f);                             // :119-134 (`static bool even`)
+        // :117 inject_inputs, :119-134 teacher forcing on alternate passes (`static bool even`), :136-141 traversal,
+        // :143-186 read-out + loss/reward — one enqueue, one synchronisation
+        std::vector<float> smooth = brain_->engine_step(in, expected, INPUT_RATE_HZ, even_ ? 1.0f : 0.0f);
         even_ = !even_;
-        brain_->encode_traversal();                                                       // :136-141
         ++step_;
-        std::vector<float> smooth = brain_->readout_filtered(&expected);                  // :143-186 (synchronises)
         if (logger_) {
             if (step_ % 100 == 0) logger_->log_samples(in, smooth);                       // :166-168
             if (rewardWindow_ && step_ % rewardWindow_ == 0) {                            // :173-186 (loss computed on the device)

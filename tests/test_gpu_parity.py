@@ -303,6 +303,31 @@ def test_parallel_conflict_free_is_bit_exact():
         assert_same_state(b, o, f"clock mode {clock_mode}")
 
 
+def test_engine_step_graph_replay_is_bit_exact():
+    """abnn_engine_step (stage frame + inject + teacher forcing + pass + read-out as one call, recorded into a CUDA
+    graph on the second call and replayed afterwards) on a conflict-free PARALLEL workload: every pass equals
+    the oracle driven by the separate calls, bit for bit, and the replay really happened."""
+    rng = np.random.default_rng(12)
+    N = 1 << 15
+    syn = np.zeros(N, O.SYN_DTYPE)
+    syn["src"] = rng.integers(0, N, N); syn["dst"] = rng.permutation(N)
+    syn["w"] = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    pre = rng.integers(1, 30_000, N).astype(np.uint64)
+    over = dict(n_input=64, n_output=64, n_hidden=N - 128, n_syn=N, sampler=capi.SAMPLER_SWEEP, exec_mode=capi.EXEC_PARALLEL,
+                window_pre=60_000, refractory=20_000, reward_window=3)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(pre, None); x.clock = 30_001; x.set_reward(0.3)
+    stim = FunctionalDataset(64, 64)
+    for p in range(8):
+        vin, exp = stim.nextInput(), stim.nextExpected()
+        rb = b.engine_step(vin, exp, 1000.0, float(p & 1), N, want_rates=True)
+        o.inject_inputs(vin, 1000.0); o.teacher_force(exp, float(p & 1)); o.run_pass(N)
+        assert rb.tobytes() == o.readout_filtered(exp).tobytes(), f"pass {p}"
+    assert_same_state(b, o, "after 8 engine steps")
+    assert b.get_loss() == o.get_loss() and o.get_loss()[1] == 2
+
+
 def test_parallel_statistical_parity_toy():
     """configs[0] at full size (1M synapses, 1M-event passes), fully parallel. Bounds: gated and fired
     counts within 6 % of the oracle's (+ 5 sigma Poisson; the library keeps at most 1/16 of a pass in
