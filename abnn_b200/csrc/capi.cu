@@ -534,7 +534,8 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
         const bool miss_normal = getenv("ABNN_L2_MISS") && atoi(getenv("ABNN_L2_MISS")) == 1;
         // default: slack32 + lastVisited (60 MB at 5M neurons) / LIVE view: lastFired + lastVisited
         const u64 hot_words = snap ? (n_arr <= 1 ? 1 : n_arr == 2 ? 3 : 5) : (n_arr <= 1 ? 2 : 4);
-        const size_t hot = (size_t)hot_words * npad * sizeof(u32);
+        size_t hot = (size_t)hot_words * npad * sizeof(u32);
+        if (getenv("ABNN_L2_EXTRA_MB")) hot += (size_t)atoi(getenv("ABNN_L2_EXTRA_MB")) << 20;   // measurements: reach into the next array
         size_t want = std::min<size_t>(hot, (size_t)max_persist);
         if (getenv("ABNN_L2_CARVE_MAX")) want = (size_t)max_persist;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
