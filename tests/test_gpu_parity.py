@@ -463,3 +463,59 @@ def test_engine_loop_matches_oracle_per_pass_clock():
         assert rb.tobytes() == ro.tobytes(), f"pass {p}"
     assert b.get_loss() == o.get_loss() and o.get_loss()[1] == 3
     assert_same_state(b, o)
+
+
+# ---- edge cases: empty and ragged inputs, error behaviour ------------------------------------------------------
+@pytest.mark.parametrize("mode", [capi.EXEC_SERIAL, capi.EXEC_EXACT, capi.EXEC_PARALLEL])
+def test_ragged_and_empty_passes(mode):
+    """Table length not a multiple of the line (13 records), passes of 0, 1, 7, 255, 257 and 1000 events: counts,
+    lastVisited and (SERIAL/EXACT) the whole state match the oracle; an empty table and a zero-event pass are no-ops."""
+    rng = np.random.default_rng(8)
+    N, n = 40, 13
+    syn = random_graph(rng, n, N, 0.5, 1.0)
+    over = dict(n_input=4, n_output=4, n_hidden=N - 8, n_syn=n, exec_mode=mode, sample_block=8, table_order=capi.TABLE_DST_SORTED,
+                window_pre=10**6, refractory=50)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_timestamps(np.full(N, 5, np.uint64), None); x.clock = 100
+    for x in (b, o):                                   # empty table: every event is skipped
+        st = x.run_pass(300)
+        assert (st.gated, st.fired, st.candidates) == (0, 0, 0)
+    b.upload_synapses(syn); o.upload_synapses(syn)
+    total = 0
+    for events in (0, 1, 7, 255, 257, 1000):
+        sb, so = b.run_pass(events), o.run_pass(events)
+        assert sb.events == so.events == events
+        if mode == capi.EXEC_PARALLEL:
+            assert sb.candidates == so.candidates or total > 0      # fires of earlier passes may differ
+            assert np.array_equal(b.timestamps()[1], o.timestamps()[1])
+        else:
+            assert_same_stats(sb, so, f"{events} events")
+        total += so.gated
+    assert total > 100
+    if mode != capi.EXEC_PARALLEL:
+        assert_same_state(b, o)
+
+
+def test_error_behaviour():
+    """Bad arguments come back as status codes with a message; nothing throws across the ABI, the handle stays usable."""
+    import ctypes as C
+    p = O.default_params(capi.PROFILE_NORTH_STAR, n_input=8, n_output=8, n_hidden=100, n_syn=1000, syn_capacity=1000)
+    with Brain(p) as b:
+        with pytest.raises(capi.AbnnError) as e:
+            b.inject_inputs(np.zeros(7, np.float32), 1000.0)                 # brain.cpp:75 expects n_input values
+        assert e.value.status == capi.ERR_INVALID
+        with pytest.raises(capi.AbnnError) as e:
+            b.upload_synapses(np.zeros(1001, O.SYN_DTYPE))
+        assert e.value.status == capi.ERR_CAPACITY
+        with pytest.raises(capi.AbnnError) as e:
+            b.load("/nonexistent/model.bnn")
+        assert e.value.status == capi.ERR_IO
+        b.build_random_graph(1)
+        assert b.run_pass(500).events == 500
+    for bad in (dict(sample_block=3), dict(exec_mode=7), dict(world_size=2, rank=2), dict(exec_mode=capi.EXEC_EXACT, src_view=capi.SRC_LIVE),
+                dict(table_order=9)):
+        q = O.default_params(capi.PROFILE_NORTH_STAR, n_input=8, n_output=8, n_hidden=100, n_syn=1000, **bad)
+        h = C.c_void_p()
+        assert capi.load().abnn_create(C.byref(q), C.byref(h)) in (capi.ERR_INVALID, capi.ERR_UNSUPPORTED), bad
+        assert not h.value
