@@ -450,10 +450,16 @@ cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* s
 // (Also measured and dropped: one cp.async.bulk (TMA) + mbarrier per line with an L2 evict_first
 // policy — 7 % slower than LDGSTS at equal depth.)
 #ifndef ABNN_LINE_MIN_CTAS
-#define ABNN_LINE_MIN_CTAS 3
+#define ABNN_LINE_MIN_CTAS 4
+#endif
+#ifndef ABNN_LINE_PART
+#define ABNN_LINE_PART 4                 // steps whose gate / lastFired reads are in flight together (8, 4 or 2)
 #endif
 constexpr int LINE_STAGE_BYTES = 32 * 128;
-constexpr int LINE_WARPS = 8;
+#ifndef ABNN_LINE_WARPS
+#define ABNN_LINE_WARPS 8
+#endif
+constexpr int LINE_WARPS = ABNN_LINE_WARPS;
 constexpr u32 LINE_FIRE_CAP = 16;       // fires of one chunk kept in shared memory for the chunk's later steps
 constexpr size_t LINE_WARP_SMEM = LINE_STAGE_BYTES + 256 + LINE_FIRE_CAP * (sizeof(u64) + sizeof(u32)) + 64;   // 4608
 constexpr size_t LINE_SMEM = LINE_WARPS * LINE_WARP_SMEM;
@@ -467,9 +473,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int VISITS, int SLACK>
-__global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const __grid_constant__ KParams kp, const DevPtrs d)
+__global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_traverse_line(const __grid_constant__ KParams kp, const DevPtrs d)
 {
-    constexpr int LOGB = 3, B = 8;
+    constexpr int LOGB = 3, B = 8, PART = ABNN_LINE_PART;
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -538,62 +544,70 @@ __global__ void __launch_bounds__(256, ABNN_LINE_MIN_CTAS) k_traverse_line(const
         cp_async_wait<0>();
         __syncwarp();                                        // the other lanes' copies have landed too
 
-        // ---- A: gate and lastFired[dst] reads in flight ---------------------------------------------
-        u64 ts[B];                                           // lastFired[dst] (SLACK) / lastFired[src], then [dst]
-        u32 gate[B];                                         // SLACK: v[src]
+        // ---- A + B, ABNN_LINE_PARTS steps at a time (fewer live registers -> 4 CTAs per SM) ----------------
+        u32 candm = 0, nC = 0;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            ts[k] = 0; gate[k] = 0;
-            if ((okm >> k) & 1u) {
-                const uint2 sd = *reinterpret_cast<const uint2*>(mine + k * 512);
-                if (SLACK) {
-                    gate[k] = __ldcg(d.slack + sd.x);                                       // brain.metal:73 (32-bit form)
-                    ts[k] = __ldcg(d.live + sd.y);                                          // brain.metal:79
-                } else {
-                    ts[k] = __ldcg(d.view + sd.x);                                          // brain.metal:73
+        for (int k0 = 0; k0 < B; k0 += PART) {
+            // A: gate and lastFired[dst] reads in flight
+            u64 ts[PART];                                    // lastFired[dst] (SLACK) / lastFired[src], then [dst]
+            u32 gate[PART];                                  // SLACK: v[src]
+#pragma unroll
+            for (int j = 0; j < PART; ++j) {
+                const int k = k0 + j;
+                ts[j] = 0; gate[j] = 0;
+                if ((okm >> k) & 1u) {
+                    const uint2 sd = *reinterpret_cast<const uint2*>(mine + k * 512);
+                    if (SLACK) {
+                        gate[j] = __ldcg(d.slack + sd.x);                                   // brain.metal:73 (32-bit form)
+                        ts[j] = __ldcg(d.live + sd.y);                                      // brain.metal:79
+                    } else {
+                        ts[j] = __ldcg(d.view + sd.x);                                      // brain.metal:73
+                    }
                 }
             }
-        }
-        u32 candm = 0;
-        if (SLACK) {
-            u32 exact = 0;
+            if (SLACK) {
+                u32 exact = 0;
 #pragma unroll
-            for (int k = 0; k < B; ++k) {
-                candm |= (u32)(((okm >> k) & 1u) && t0 + (k * 32 + lane) * tick < gate[k]) << k;   // brain.metal:74
-                exact |= (u32)(gate[k] == SLACK_EXACT) << k;
-            }
-            if (__any_sync(0xffffffffu, exact & okm)) {      // snapshot in the future of the pass start: exact 64-bit test
+                for (int j = 0; j < PART; ++j) {
+                    const int k = k0 + j;
+                    candm |= (u32)(((okm >> k) & 1u) && t0 + (k * 32 + lane) * tick < gate[j]) << k;   // brain.metal:74
+                    exact |= (u32)(gate[j] == SLACK_EXACT) << k;
+                }
+                if (__any_sync(0xffffffffu, exact & okm)) {  // snapshot in the future of the pass start: exact 64-bit test
 #pragma unroll
-                for (int k = 0; k < B; ++k)
-                    if (((exact & okm) >> k) & 1u) {
-                        const u64 now = now0 + (u64)((k * 32 + lane) * tick);
-                        const bool cand = now - __ldcg(d.view + *reinterpret_cast<const u32*>(mine + k * 512)) <= kp.window_pre;
-                        candm = (candm & ~(1u << k)) | ((u32)cand << k);
+                    for (int j = 0; j < PART; ++j) {
+                        const int k = k0 + j;
+                        if (((exact & okm) >> k) & 1u) {
+                            const u64 now = now0 + (u64)((k * 32 + lane) * tick);
+                            const bool cand = now - __ldcg(d.view + *reinterpret_cast<const u32*>(mine + k * 512)) <= kp.window_pre;
+                            candm = (candm & ~(1u << k)) | ((u32)cand << k);
+                        }
                     }
-            }
-        } else {
+                }
+            } else {
 #pragma unroll
-            for (int k = 0; k < B; ++k) {                    // 64-bit gate: window test, then lastFired[dst] reads in flight
+                for (int j = 0; j < PART; ++j) {             // 64-bit gate: window test, then lastFired[dst] reads in flight
+                    const int k = k0 + j;
+                    const u64 now = now0 + (u64)((k * 32 + lane) * tick);
+                    const bool cand = ((okm >> k) & 1u) && (now - ts[j] <= kp.window_pre || (!kp.snapshot && ts[j] > now));   // brain.metal:74
+                    ts[j] = now;
+                    if (cand) { candm |= 1u << k; ts[j] = __ldcg(d.live + *reinterpret_cast<const u32*>(mine + k * 512 + 4)); }   // brain.metal:79
+                }
+            }
+            // B: lastVisited, refractory gate, compaction of the open events
+#pragma unroll
+            for (int j = 0; j < PART; ++j) {
+                const int k = k0 + j;
                 const u64 now = now0 + (u64)((k * 32 + lane) * tick);
-                const bool cand = ((okm >> k) & 1u) && (now - ts[k] <= kp.window_pre || (!kp.snapshot && ts[k] > now));   // brain.metal:74
-                ts[k] = now;
-                if (cand) { candm |= 1u << k; ts[k] = __ldcg(d.live + *reinterpret_cast<const u32*>(mine + k * 512 + 4)); }   // brain.metal:79
+                if (VISITS) visit(d, (okm >> k) & 1u, *reinterpret_cast<const u32*>(mine + k * 512 + 4), now);   // README.md:84
+                const u64 gap = ts[j] <= now ? now - ts[j] : ts[j] - now;
+                const bool open = ((candm >> k) & 1u) && gap > kp.refractory;               // brain.metal:79-83
+                const unsigned cm = __ballot_sync(0xffffffffu, open);
+                if (open) queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
+                nC += __popc(cm);
             }
         }
         n_cand += __popc(candm);
-
-        // ---- B: lastVisited, refractory gate, compaction of the open events ----------------------------
-        u32 nC = 0;
-#pragma unroll
-        for (int k = 0; k < B; ++k) {
-            const u64 now = now0 + (u64)((k * 32 + lane) * tick);
-            if (VISITS) visit(d, (okm >> k) & 1u, *reinterpret_cast<const u32*>(mine + k * 512 + 4), now);   // README.md:84
-            const u64 gap = ts[k] <= now ? now - ts[k] : ts[k] - now;
-            const bool open = ((candm >> k) & 1u) && gap > kp.refractory;                   // brain.metal:79-83
-            const unsigned cm = __ballot_sync(0xffffffffu, open);
-            if (open) queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
-            nC += __popc(cm);
-        }
         __syncwarp();
 
         // ---- C: dense steps over the queue ----------------------------------------------------------------
@@ -711,14 +725,14 @@ static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count
     }
     if (!kp.count || !kp.n_local) return cudaSuccess;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line<VISITS, SLACK>, 256, LINE_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line<VISITS, SLACK>, LINE_WARPS * 32, LINE_SMEM);
     if (per_sm < 1) per_sm = 1;
     if (bps > 0 && bps < per_sm) per_sm = bps;
     const u64 chunks = (kp.count + 255) / 256;
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
     if (grid > chunks / (LINE_WARPS * 16) + 1) grid = chunks / (LINE_WARPS * 16) + 1;   // in-flight window <= 1/16 of the pass
-    k_traverse_line<VISITS, SLACK><<<(unsigned)grid, 256, LINE_SMEM, st>>>(kp, d);
+    k_traverse_line<VISITS, SLACK><<<(unsigned)grid, LINE_WARPS * 32, LINE_SMEM, st>>>(kp, d);
     return cudaGetLastError();
 }
 
