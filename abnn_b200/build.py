@@ -17,7 +17,6 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("ABNN_B200_OUT") or os.path.join(HERE, "libabnn_b200.so")   # override: tuning variants only
 OBJ = os.path.join(HERE, "_obj" + os.environ.get("ABNN_B200_OBJ_SUFFIX", ""))
 SOURCES = ["traversal.cu", "exact.cu", "io_kernels.cu", "structural.cu", "init.cu", "capi.cu"]
-HOST_SOURCES = ["brain.cpp", "brain_engine.cpp", "manifest.cpp", "engine_capi.cpp"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false",
               "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
@@ -32,9 +31,6 @@ def _nvcc() -> str:
 
 def _deps():
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    host = os.path.join(HERE, "host")
-    if os.path.isdir(host):
-        files += [os.path.join(host, f) for f in os.listdir(host)]
     files.append(os.path.join(HERE, "..", "include", "abnn.h"))
     files.append(os.path.abspath(__file__))
     return files
@@ -60,15 +56,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
             continue
         obj = os.path.join(OBJ, src + ".o")
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("ABNN_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src in HOST_SOURCES:
-        path = os.path.join(HERE, "host", src)
-        if not os.path.exists(path):
-            continue
-        obj = os.path.join(OBJ, src + ".o")
-        cmd = [nvcc, "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-Wall", "-I", os.path.join(HERE, "..", "include"),
-               "-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -136,7 +136,7 @@ def stimulus_frames(n):
     return np.stack(fin), np.stack(fex)
 
 
-def base_params(args, O, capi, rank, world, events):
+def base_params(args, capi, rank, world, events):
     # North-star profile; the pre-spike window / refractory period are the reference's 5 / 2 PASSES
     # (brain.metal:23-24) expressed in per-event ticks (one pass = `events` ticks).
     over = dict(n_input=N_IN, n_output=N_OUT, n_hidden=args.hidden, n_syn=args.syn, seed=42,
@@ -146,7 +146,10 @@ def base_params(args, O, capi, rank, world, events):
                 rank=rank, world_size=world, device=-1, sample_block=args.block,
                 table_order=capi.TABLE_DST_SORTED if args.table_order == "dst" else capi.TABLE_AS_GIVEN,
                 src_view=capi.SRC_SNAPSHOT if args.src_view == "snapshot" else capi.SRC_LIVE)
-    return O.default_params(capi.PROFILE_NORTH_STAR, **over)
+    p = capi.default_params(capi.PROFILE_NORTH_STAR)           # the library's own defaults (abnn_default_params)
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
 
 
 def warm_timestamps(n_neuron, frac, events, seed=7):
@@ -167,7 +170,7 @@ def run_cpu(args, steps, warmup, as_reference):
     from oracle import pyoracle as O
     T = os.cpu_count() or 1
     syn, events = args.cpu_syn, args.cpu_events
-    p = base_params(args, O, capi, 0, 1, events)
+    p = base_params(args, capi, 0, 1, events)
     p.n_syn = syn
     p.exec_mode = capi.EXEC_SERIAL
     world = O.OracleWorld(p, T)
@@ -213,7 +216,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "synaptic events/sec", "value": val, "unit": "events/s", "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u64 timestamps + f32 weights", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u64 timestamps, f32 weights", "data": "synthetic",
             "config": {"workload": workload, "sampler": args.sampler, "l2": "inputs larger than L2"},
             "cpu_baseline": {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample,
                              "gated_fraction": g},
@@ -224,12 +227,11 @@ def main():
     import torch
     import torch.distributed as dist
     from abnn_b200 import Brain, capi
-    from oracle import pyoracle as O      # parameter defaults + cpu_baseline leg only
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    p = base_params(args, O, capi, rank, world, args.events)
+    p = base_params(args, capi, rank, world, args.events)
     p.device = local_rank
     b = Brain(p)
     if world > 1:
@@ -335,7 +337,7 @@ def main():
         line = {
             "metric": "synaptic events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64 timestamps + f32 weights", "data": "synthetic",
+            "dtype": "u64 timestamps, f32 weights", "data": "synthetic",
             "config": {"workload": workload, "sampler": args.sampler, "sample_block": args.block, "table_order": args.table_order, "exec_mode": "parallel", "clock": "per_event",
                        "graph": "ER endpoints, Beta(2,8) weights (Philox)", "window_pre_passes": 5, "refractory_passes": 2,
                        "warm_fraction": args.warm_frac, "track_visits": not args.no_visits,
