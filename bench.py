@@ -217,7 +217,10 @@ def main():
             "impl": "reference", "metric": "synaptic events/sec", "value": val, "unit": "events/s", "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64 timestamps, f32 weights", "data": "synthetic",
-            "config": {"workload": workload, "sampler": args.sampler, "l2": "inputs larger than L2"},
+            "config": {"workload": workload, "sampler": args.sampler, "sample_block": args.block, "table_order": args.table_order,
+                       "exec_mode": "serial per dst-shard (oracle), one shard per host thread", "clock": "per_event",
+                       "graph": "ER endpoints, Beta(2,8) weights (Philox)", "window_pre_passes": 5, "refractory_passes": 2,
+                       "warm_fraction": args.warm_frac, "track_visits": not args.no_visits, "l2": "inputs larger than L2"},
             "cpu_baseline": {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample,
                              "gated_fraction": g},
             "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
