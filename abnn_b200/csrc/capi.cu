@@ -1004,12 +1004,12 @@ int abnn_get_reward(abnn_handle* h, float* reward, float* rbar)
 
 // Everything one pass enqueues on the handle's stream. Capture-safe for PARALLEL execution (no host
 // synchronisation, no allocation): abnn_engine_step records it into a CUDA graph.
-static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t after_traverse)
+static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t after_traverse, bool head_refreshed = false)
 {
     if (slack_mode(h, kp)) {
         kp.use_slack = 1;
         if (h->slack_ready) {           // the exchange delivered the gate words; inject / teacher forcing touched the head since
-            CU(launch_build_slack(kp, h->d, h->d.view, 0, (u64)h->p.n_input + h->p.n_output, h->st));
+            if (!head_refreshed) CU(launch_build_slack(kp, h->d, h->d.view, 0, (u64)h->p.n_input + h->p.n_output, h->st));
         } else {
             RET(ensure_view(h));
             CU(launch_build_slack(kp, h->d, h->d.view, 0, h->N, h->st));
@@ -1061,10 +1061,9 @@ static ReadoutParams readout_params(const abnn_handle* h)
 static int enqueue_step(abnn_handle* h, const KParams& kp)
 {
     const u32 ni = h->p.n_input, no = h->p.n_output;
-    const float* scal = h->d_frame + ni + no;
-    CU(launch_inject(kp, h->d, h->d_frame, ni, 0.f, scal, h->st));
-    CU(launch_teacher(kp, h->d, h->d_frame + ni, no, 0.f, h->p.teacher_gap, scal + 1, h->st));
-    RET(enqueue_pass(h, kp, nullptr));
+    const bool refresh = slack_mode(h, kp) && h->slack_ready;
+    CU(launch_step_prologue(kp, h->d, h->d_frame, ni, no, h->p.teacher_gap, refresh, h->st));
+    RET(enqueue_pass(h, kp, nullptr, refresh));
     CU(launch_readout(kp, h->d, readout_params(h), h->rs, h->d_frame + ni, h->st));
     return 0;
 }

@@ -50,6 +50,19 @@ __host__ __device__ __forceinline__ float rand01_xorshift(u32 s)
     return (float)(s & 0xFFFFFFu) * (1.0f / 16777216.0f);
 }
 
+// 32-bit pre-spike gate word of a neuron for the pass that starts at `clock` (traversal.cu:k_build_slack):
+// an event with tick offset t = now - clock passes the window gate (brain.metal:73-77) iff t < word.
+// 0 = never in this pass, 0xFFFFFFFE = always, 0xFFFFFFFF = snapshot in the future: take the exact 64-bit test.
+constexpr u32 SLACK_EXACT = 0xFFFFFFFFu;
+__host__ __device__ __forceinline__ u32 slack_word(u64 clock, u64 last_fired, u64 window_pre)
+{
+    if (last_fired > clock) return SLACK_EXACT;
+    const u64 age = clock - last_fired;
+    if (age > window_pre) return 0u;
+    const u64 room = window_pre - age;
+    return room >= 0xFFFFFFFDull ? 0xFFFFFFFEu : (u32)room + 1u;
+}
+
 // Growth candidate staged by a firing event; appended in `order` by the structural step.
 struct GrowCand { u64 order; u32 src, dst; };
 

@@ -41,6 +41,34 @@ __global__ void k_teacher(const __grid_constant__ KParams kp, const DevPtrs d, c
     }
 }
 
+// abnn_engine_step prologue: inject_inputs + teacher forcing in one launch over the n_in + n_out head neurons
+// (frame = [in | expected | pTick | rate] in device memory), and — when the exchange already delivered the
+// gate words of this pass — the refresh of the head's words, which these two steps may just have changed.
+__global__ void k_step_prologue(const __grid_constant__ KParams kp, const DevPtrs d, const float* __restrict__ frame,
+                                u32 n_in, u32 n_out, u64 gap, u32 refresh_slack)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in + n_out) return;
+    const u64 now = d.sc->clock, pass = d.sc->pass_index;
+    const float pTick = frame[n_in + n_out], rate = frame[n_in + n_out + 1];
+    u64 lp = d.view[i];
+    bool spike;
+    if (i < n_in) {                                                        // brain.cpp:73-83
+        const Philox4 r = philox4x32_10((u32)pass, (u32)(pass >> 32), i, STREAM_INJECT, kp.seed_lo, kp.seed_hi);
+        spike = u01_24(r.x) < pTick * frame[i];
+    } else {                                                               // brain-engine.cpp:126-133
+        const u32 o = i - n_in;
+        const Philox4 r = philox4x32_10((u32)pass, (u32)(pass >> 32), o, STREAM_TEACHER, kp.seed_lo, kp.seed_hi);
+        spike = u01_24(r.x) < frame[i] * rate && (now - lp > gap);
+    }
+    if (spike) {
+        lp = now;
+        d.view[i] = now;
+        if (i >= kp.neuron_lo && i < kp.neuron_hi) d.live[i] = now;
+    }
+    if (refresh_slack) d.slack[i] = slack_word(now, lp, kp.window_pre);
+}
+
 // Brain::read_outputs (brain.cpp:145-157), window = ticks of the last pass.
 __device__ __forceinline__ bool output_spiked(const KParams& kp, const DevPtrs& d, u32 o)
 {
@@ -126,6 +154,13 @@ cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* exp
 {
     if (!n) return cudaSuccess;
     k_teacher<<<(n + 255) / 256, 256, 0, st>>>(kp, d, expected, n, rate, gap, scal);
+    return cudaGetLastError();
+}
+cudaError_t launch_step_prologue(const KParams& kp, const DevPtrs& d, const float* frame, u32 n_in, u32 n_out, u64 gap,
+                                 bool refresh_slack, cudaStream_t st)
+{
+    if (!(n_in + n_out)) return cudaSuccess;
+    k_step_prologue<<<(n_in + n_out + 255) / 256, 256, 0, st>>>(kp, d, frame, n_in, n_out, gap, refresh_slack ? 1u : 0u);
     return cudaGetLastError();
 }
 cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st)

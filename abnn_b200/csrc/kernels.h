@@ -31,6 +31,9 @@ struct ReadoutState { float* rate; float* iir; float* fir; float* smooth; unsign
 cudaError_t launch_inject(const KParams& kp, const DevPtrs& d, const float* v, u32 n, float pTick, const float* scal, cudaStream_t st);
 cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* expected, u32 n, float rate, u64 gap, const float* scal,
                            cudaStream_t st);
+// inject + teacher forcing (+ gate-word refresh of the head) in one launch; frame = [in | expected | pTick | rate]
+cudaError_t launch_step_prologue(const KParams& kp, const DevPtrs& d, const float* frame, u32 n_in, u32 n_out, u64 gap,
+                                 bool refresh_slack, cudaStream_t st);
 cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st);
 cudaError_t launch_readout(const KParams& kp, const DevPtrs& d, const ReadoutParams& rp, const ReadoutState& rs,
                            const float* expected, cudaStream_t st);

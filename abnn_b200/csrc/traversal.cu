@@ -395,20 +395,11 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
 // is what lets it stay L2-resident next to lastVisited/lastFired under the 1B-synapse stream.
 // 0xFFFFFFFF marks the (pathological) neurons whose snapshot lies in the future of the pass start;
 // for those the kernel falls back to the exact 64-bit test.
-constexpr u32 SLACK_EXACT = 0xFFFFFFFFu;
 __global__ void __launch_bounds__(256) k_build_slack(const __grid_constant__ KParams kp, const DevPtrs d, const u64* src, u64 n0, u64 n1)
 {
     const u64 clock = d.sc->clock;
     for (u64 n = n0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (u64)gridDim.x * blockDim.x) {
-        const u64 lp = src[n];
-        u32 v;
-        if (lp > clock) v = SLACK_EXACT;
-        else {
-            const u64 age = clock - lp;
-            if (age > kp.window_pre) v = 0;
-            else { const u64 room = kp.window_pre - age; v = room >= 0xFFFFFFFDull ? 0xFFFFFFFEu : (u32)room + 1u; }
-        }
-        d.slack[n] = v;
+        d.slack[n] = slack_word(clock, src[n], kp.window_pre);
     }
 }
 cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* src, u64 n0, u64 n1, cudaStream_t st)

@@ -362,9 +362,10 @@ def main():
                          "sector_level_frac": ev_per_launch * (32.0 + 32.0 * g) / (trav_mean * 1e-3) / 1e9 / peak},
             "e2e": {"value": args.events * K / e2e_s, "unit": "events/s",
                     "h2d_bytes_per_step": int((N_IN + N_OUT + 2) * 4), "d2h_bytes_per_step": int(N_OUT * 4)},
-            # per step (one CUDA-graph launch): k_inject, k_teacher, k_build_slack, traversal kernel, k_end_pass, k_readout
-            # (+ N>1: k_build_slack on the owned slice; the snapshot copy / NCCL kernels are not counted)
-            "gpu_launches": (6 if world == 1 else 7) * K,
+            # per step (abnn_engine_step; one CUDA-graph launch at N=1): k_step_prologue (inject + teacher forcing), k_build_slack
+            # (all neurons at N=1, the owned slice at N>1), traversal kernel, k_end_pass, k_readout; the snapshot copy / NCCL
+            # kernels are not counted
+            "gpu_launches": 5 * K,
             "clocks": clocks,
         }
         if world == 1 and not args.skip_cpu:
