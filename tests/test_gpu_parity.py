@@ -519,3 +519,41 @@ def test_error_behaviour():
         h = C.c_void_p()
         assert capi.load().abnn_create(C.byref(q), C.byref(h)) in (capi.ERR_INVALID, capi.ERR_UNSUPPORTED), bad
         assert not h.value
+
+
+# ---- full size (BASELINE.json configs[1]): size-independent properties --------------------------------------------------
+def test_full_size_parallel_vs_exact_properties():
+    """configs[1] — 5,000,000 hidden, 100,000,000 synapses, 150,000,000-event passes, line sampler over the dst-sorted
+    table. The oracle would need minutes here, so the throughput kernel (PARALLEL) is checked against the EXACT mode
+    (itself bit-identical to the oracle at the sizes above) through properties that do not depend on execution order:
+    the same table after init + sort, the same pre-spike candidates in the first pass, identical lastVisited after every
+    pass (an order-free max over the sampled events), and gated / fired counts and mean weight within 1 %."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 40 * 2**30:
+        pytest.skip("needs 40 GB of free device memory")
+    events = 150_000_000
+    over = dict(n_input=256, n_output=256, n_hidden=5_000_000, n_syn=100_000_000, sample_block=8, table_order=capi.TABLE_DST_SORTED,
+                window_pre=5 * events, refractory=2 * events, seed=42)
+    n = 5_000_512
+    rng = np.random.default_rng(7)
+    lf = np.zeros(n, np.uint64)
+    idx = rng.choice(n, size=n // 4, replace=False)
+    lf[idx] = rng.integers(events, 6 * events, size=len(idx)).astype(np.uint64)
+    res = {}
+    for mode in (capi.EXEC_EXACT, capi.EXEC_PARALLEL):
+        with Brain(O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=mode, **over)) as b:
+            b.init_graph(capi.GRAPH_ER_BETA, 1)
+            b.upload_timestamps(lf, None); b.clock = 6 * events; b.set_reward(0.01)
+            stats = [b.run_pass(events) for _ in range(2)]
+            syn = b.download_synapses()
+            assert np.all(np.diff(syn["dst"].astype(np.int64)) >= 0)
+            res[mode] = (stats, b.timestamps()[1], float(syn["w"].mean(dtype=np.float64)),
+                         int(syn["src"].astype(np.uint64).sum()), int(syn["dst"].astype(np.uint64).sum()))
+    (se, lve, we, srce, dste), (sp, lvp, wp, srcp, dstp) = res[capi.EXEC_EXACT], res[capi.EXEC_PARALLEL]
+    assert (srce, dste) == (srcp, dstp)                                  # same graph
+    assert se[0].candidates == sp[0].candidates > 10_000_000             # same events, same gate decisions
+    assert np.array_equal(lve, lvp), "lastVisited differs between EXACT and PARALLEL at full size"
+    for a, b_ in zip(se, sp):
+        assert a.events == b_.events == events
+        assert abs(a.gated - b_.gated) <= 0.01 * a.gated and abs(a.fired - b_.fired) <= 0.01 * a.fired + 100, (a.gated, b_.gated, a.fired, b_.fired)
+    assert abs(we - wp) < 1e-4 * we
