@@ -1316,7 +1316,8 @@ int abnn_download_gate_words(abnn_handle* h, uint32_t* words, uint32_t* valid_ou
 {
     RET(use(h));
     if (valid_out) *valid_out = h->slack_ready ? 1u : 0u;
-    if (!h->d.slack || !words) return h->d.slack || !words ? 0 : fail(ABNN_ERR_UNSUPPORTED, "this handle has no gate words (LIVE src view)");
+    if (!words) return 0;
+    if (!h->d.slack) return fail(ABNN_ERR_UNSUPPORTED, "this handle has no gate words (LIVE src view)");
     CU(cudaMemcpyAsync(words, h->d.slack, h->N * sizeof(u32), cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     return 0;

@@ -706,13 +706,16 @@ template <int VISITS, int SLACK>
 static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
-    static bool configured = false;
-    if (!configured) {
+    // function attributes are per device: one process may own handles on several GPUs
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
         if (e != cudaSuccess) return e;
         if (getenv("ABNN_LINE_CARVEOUT"))      // measurements only: shared-memory share of the L1/shared array, percent
             cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("ABNN_LINE_CARVEOUT")));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     if (!kp.count || !kp.n_local) return cudaSuccess;
     int per_sm = 0;
@@ -722,7 +725,7 @@ static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count
     const u64 chunks = (kp.count + 255) / 256;
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
-    if (grid > chunks / (LINE_WARPS * 16) + 1) grid = chunks / (LINE_WARPS * 16) + 1;   // in-flight window <= 1/16 of the pass
+    if (grid > chunks / (LINE_WARPS * 64) + 1) grid = chunks / (LINE_WARPS * 64) + 1;   // in-flight window <= 1/64 of the pass
     k_traverse_line<VISITS, SLACK><<<(unsigned)grid, LINE_WARPS * 32, LINE_SMEM, st>>>(kp, d);
     return cudaGetLastError();
 }

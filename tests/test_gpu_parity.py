@@ -356,6 +356,40 @@ def test_parallel_statistical_parity_toy():
     assert np.array_equal(b.timestamps()[1], o.timestamps()[1])
 
 
+def test_parallel_deviation_across_seeds():
+    """SURVEY.md §8c asks for PARALLEL bounds relative to the oracle's own run-to-run spread. configs[0] shape, line
+    sampler, dst-sorted table, 8 Philox seeds, 3 passes each. Measured here: the oracle's seed-to-seed spread of the
+    fire and gated counts is 0.2 %; PARALLEL sits 0.9–1.0 % above the oracle for EVERY seed — a bias, not noise: the
+    line kernel keeps 1/64 of a pass in flight unordered (16k ticks at this toy shape) against a refractory period of
+    100k ticks, so an event can run before the fire of the same neuron that precedes it in event order (with 1/16 of a
+    pass in flight the bias was 3.7 %). At the benchmark shape the in-flight window is 0.8 % of a pass against a
+    refractory period of two passes (test_full_size_parallel_vs_exact_properties: below 1 %). Bounds asserted: every
+    seed within 2 %, and the deviations of the 8 seeds within 0.5 % of each other (a property of the schedule, not of
+    the seed)."""
+    fired_o, fired_b, gated_o, gated_b = [], [], [], []
+    for seed in range(100, 108):
+        over = dict(TOY, exec_mode=capi.EXEC_PARALLEL, sample_block=8, table_order=capi.TABLE_DST_SORTED,
+                    window_pre=2_000_000, refractory=100_000, seed=seed)
+        b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+        b.init_graph(capi.GRAPH_ER_BETA, 3); o.init_graph(capi.GRAPH_ER_BETA, 3)
+        pre = np.random.default_rng(5).integers(1, 1_000_000, 10_512).astype(np.uint64)
+        fb = fo = gb = go = 0
+        for x in (b, o):
+            x.upload_timestamps(pre, None); x.clock = 1_000_000; x.set_reward(0.05)
+        for p in range(3):
+            sb, so = b.run_pass(1_000_000), o.run_pass(1_000_000)
+            fb += sb.fired; fo += so.fired; gb += sb.gated; go += so.gated
+        fired_o.append(fo); fired_b.append(fb); gated_o.append(go); gated_b.append(gb)
+        b.close()
+    for name, ob, bb in (("fired", fired_o, fired_b), ("gated", gated_o, gated_b)):
+        ob, bb = np.array(ob, float), np.array(bb, float)
+        dev = (bb - ob) / ob
+        spread = ob.std(ddof=1) / ob.mean()
+        assert ob.min() > 1000 and spread < 0.01
+        assert np.abs(dev).max() <= 0.02, (name, dev, spread)
+        assert dev.max() - dev.min() <= 0.005, (name, dev)
+
+
 # ---- graph init / I/O ------------------------------------------------------------------------------
 def test_er_beta_init_bit_exact_and_beta_moments():
     over = dict(n_input=64, n_output=64, n_hidden=100_000, n_syn=500_000)
