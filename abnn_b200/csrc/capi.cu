@@ -343,7 +343,7 @@ uint32_t abnn_abi_version(void) { return ABNN_ABI_VERSION; }
 int abnn_default_params(abnn_params* p, uint32_t profile)
 {
     if (!p) return fail(ABNN_ERR_INVALID, "null params");
-    if (profile > ABNN_PROFILE_NORTH_STAR) return fail(ABNN_ERR_INVALID, "unknown profile");
+    if (profile > ABNN_PROFILE_B200) return fail(ABNN_ERR_INVALID, "unknown profile");
     std::memset(p, 0, sizeof(*p));
     p->struct_size = sizeof(abnn_params); p->abi_version = ABNN_ABI_VERSION;
     p->n_input = 256; p->n_output = 256; p->n_hidden = 5000000ull; p->n_syn = 1000000000ull;   // constants.h:2-5
@@ -371,6 +371,7 @@ int abnn_default_params(abnn_params* p, uint32_t profile)
     p->filter_tau = 0.02; p->dt_sec = 0.0009; p->loss0 = 0.25;
     p->device = -1; p->rank = 0; p->world_size = 1; p->l2_persist = 1;
     p->sample_block = 1;
+    if (profile == ABNN_PROFILE_B200) { p->sample_block = 8; p->table_order = ABNN_TABLE_DST_SORTED; }
     return 0;
 }
 

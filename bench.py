@@ -146,7 +146,7 @@ def base_params(args, capi, rank, world, events):
                 rank=rank, world_size=world, device=-1, sample_block=args.block,
                 table_order=capi.TABLE_DST_SORTED if args.table_order == "dst" else capi.TABLE_AS_GIVEN,
                 src_view=capi.SRC_SNAPSHOT if args.src_view == "snapshot" else capi.SRC_LIVE)
-    p = capi.default_params(capi.PROFILE_NORTH_STAR)           # the library's own defaults (abnn_default_params)
+    p = capi.default_params(capi.PROFILE_B200)                 # the library's own defaults (abnn_default_params)
     for k, v in over.items():
         setattr(p, k, v)
     return p

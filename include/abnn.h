@@ -89,7 +89,9 @@ enum abnn_table_order {     /* HBM layout of this rank's synapse table          
 };
 enum abnn_profile {
     ABNN_PROFILE_METAL_PARITY = 0, /* SWEEP, XORSHIFT, PER_PASS, SERIAL, LIVE, METAL_TID0, budget 2560 */
-    ABNN_PROFILE_NORTH_STAR   = 1  /* PHILOX, PHILOX, PER_EVENT, PARALLEL, SNAPSHOT, PASS_STEP          */
+    ABNN_PROFILE_NORTH_STAR   = 1, /* PHILOX, PHILOX, PER_EVENT, PARALLEL, SNAPSHOT, PASS_STEP          */
+    ABNN_PROFILE_B200         = 2  /* NORTH_STAR with the layout the B200 kernel is built for: sample_block 8
+                                      (one 128-byte line per draw) over a DST_SORTED table — what bench.py times */
 };
 
 /* ---- L3: every compile-time knob of the reference as a runtime parameter ------------------

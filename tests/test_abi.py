@@ -62,7 +62,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 def test_default_params_match_the_reference_constants(oracle):
     """abnn_default_params (product) against the independent restatement of constants.h in the oracle."""
-    for profile in (capi.PROFILE_METAL_PARITY, capi.PROFILE_NORTH_STAR):
+    for profile in (capi.PROFILE_METAL_PARITY, capi.PROFILE_NORTH_STAR, capi.PROFILE_B200):
         a, b = capi.default_params(profile), oracle.default_params(profile)
         assert bytes(a) == bytes(b), [n for n, _ in capi.Params._fields_ if n != "reserved_" and getattr(a, n) != getattr(b, n)]
 
