@@ -725,7 +725,17 @@ static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count
     const u64 chunks = (kp.count + 255) / 256;
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
-    if (grid > chunks / (LINE_WARPS * 64) + 1) grid = chunks / (LINE_WARPS * 64) + 1;   // in-flight window <= 1/64 of the pass
+    // Events in flight at once (grid x 8 warps x 256) execute unordered. The only cross-warp order the semantics
+    // depend on is the refractory gate (a fire blocks the later events of its neuron for `refractory` ticks), and
+    // only when the refractory period is longer than a chunk (inside a chunk the warp orders exactly): keep the
+    // in-flight window below a quarter of it. Measured at the 10k-neuron toy shape: fired count 3.7 % above the
+    // oracle with 63k ticks in flight against a 100k-tick refractory period, 1.0 % with 16k (profiles/r1_notes.md).
+    const u64 refractory_chunks = kp.refractory / (256ull * (kp.world ? kp.world : 1));
+    if (kp.clock_mode != ABNN_CLOCK_PER_PASS && refractory_chunks >= 1) {
+        u64 lim = refractory_chunks / (4 * LINE_WARPS);
+        if (lim < 1) lim = 1;
+        if (grid > lim) grid = lim;
+    }
     k_traverse_line<VISITS, SLACK><<<(unsigned)grid, LINE_WARPS * 32, LINE_SMEM, st>>>(kp, d);
     return cudaGetLastError();
 }
