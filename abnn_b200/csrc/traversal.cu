@@ -5,14 +5,15 @@
 // (README.md:77), uint64 timestamps with a per-event clock (README.md:62-63,85), lastVisited writes
 // (README.md:84), and the per-event arithmetic of brain.metal:70-126 unchanged.
 //
-//   k_traverse_line     : the throughput kernel (PHILOX sampler, sample_block = 8): every warp streams
-//                         Philox-chosen 128-byte lines of the synapse table into its own shared-memory
-//                         ring with cp.async.bulk (TMA bulk copies completing on mbarriers), so HBM
-//                         latency is hidden by the ring depth, not by registers or occupancy; per event
-//                         one L2 read of lastFired[src]; lastVisited[dst] moves with one RED.MAX.64 per
-//                         run of equal destinations (one per line when the table is dst-sorted); events
-//                         that pass the pre-spike window are resolved per destination, in event order,
-//                         inside the warp (match.any + ballot chain) and publish with 64-bit atomicMax.
+//   k_traverse_line     : the throughput kernel (PHILOX sampler, sample_block = 8): every warp copies chunks
+//                         of 32 Philox-chosen 128-byte lines of the synapse table into a 4 KB shared-memory
+//                         stage with cp.async; per event one L2 read of the 32-bit pre-spike gate word of
+//                         src; lastVisited[dst] moves with one RED.MAX.64 per run of equal destinations
+//                         (one per line when the table is dst-sorted); the events that pass the window
+//                         and the refractory gate are compacted and resolved per destination, in event
+//                         order, inside the warp (match.any + ballot chain) and publish with 64-bit
+//                         atomicMax. 32 warps per SM hide the HBM latency.
+//   k_build_slack       : the per-pass 32-bit gate words (window gate of the pass-start snapshot).
 //   k_traverse_parallel : iid PHILOX sampler (16-byte random gathers) and the SWEEP sampler.
 //   k_traverse_block    : sample_block = 2, 4, 16, 32 (register-staged).
 //   k_traverse_serial   : one thread walks the events in index order (the bit-exact order of the
@@ -420,7 +421,9 @@ cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* s
 // in flight, and then consumes the stage in three phases:
 //   A  8 steps; in step k lane l holds record (l & 7) of group 4k + (l >> 3), i.e. the warp reads 512
 //      contiguous bytes of the stage. The pre-spike gate word of src (32-bit slack, k_build_slack) and
-//      lastFired[dst] of all 8 steps are requested back to back: 16 independent L2 reads per lane.
+//      lastFired[dst] of ABNN_LINE_PART = 4 steps are requested back to back (8 independent L2 reads per
+//      lane; all 8 steps at once needs 80 registers and costs the fourth CTA per SM), then B runs on those
+//      steps, then the other four.
 //   B  8 steps: pre-spike window test (brain.metal:74), lastVisited RED once per run of equal
 //      destinations, refractory gate against the value read in A (brain.metal:79): the events that are
 //      still open are COMPACTED — their 8-bit chunk-local index goes to a shared-memory queue in event
@@ -436,8 +439,9 @@ cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* s
 // Shared memory is kept to 4.5 KB per warp on purpose. Measured on B200 (profiles/r1_notes.md): the
 // gathers of this kernel are limited by the L1's capacity to track outstanding misses, i.e. by what the
 // shared-memory carve-out leaves of the 228 KB array. A 3-deep ring (13.5 KB/warp, 16 warps) ran at
-// 3.4 ms/pass, a 2-deep ring 2.1 ms, this single stage with 24 warps 1.7 ms; forcing the carve-out to
-// 100 % shared memory took the same code from 2.1 to 3.9 ms. HBM latency is hidden across warps.
+// 3.4 ms/pass, a 2-deep ring 2.1 ms, this single stage with 24 warps 1.7 ms and with 32 warps (63
+// registers) 1.46 ms; forcing the carve-out to 100 % shared memory took the same code from 2.1 to 3.9 ms.
+// HBM latency is hidden across warps.
 // (Also measured and dropped: one cp.async.bulk (TMA) + mbarrier per line with an L2 evict_first
 // policy — 7 % slower than LDGSTS at equal depth.)
 #ifndef ABNN_LINE_MIN_CTAS
