@@ -434,7 +434,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
 
     // Random 16-byte gathers and 8-byte timestamp accesses use ONE 32-byte sector each; with the default
     // L2 fetch granularity every miss pulls 128 B from HBM (measured: 213 B of DRAM reads per event,
-    // profiles/r1_ncu_summary.md). Ask for sector-sized fetches (device-wide hint).
+    // profiles/r1_notes.md). Ask for sector-sized fetches (device-wide hint).
     if (!getenv("ABNN_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     cudaGetLastError();
 

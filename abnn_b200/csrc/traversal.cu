@@ -126,7 +126,7 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
 // atomicMax, so "the latest event wins" holds whatever the execution order.
 // (A variant that queued candidates in shared memory and processed them 32 at a time was measured
 // slower — the kernel is bound by L2 sector operations and latency, not by issue slots; see
-// profiles/r1_ncu_summary.md.)
+// profiles/r1_notes.md.)
 struct PassConsts { u64 clock, event_base, tick_base; float R, rbar; };
 
 // One candidate's turn: refractory + budget gates, release test, plasticity, timestamp write.
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
 // Block sampler (sample_block = B = 2^LOGB > 1): one Philox draw selects a block-aligned run of B
 // consecutive SynapsePacked records and B consecutive events process it. With B = 8 a draw is exactly
 // one 128-byte HBM line — the unit B200 fetches on every L2 miss whatever the load asks for — so all 8
-// records of a fetched line do work instead of 1 (profiles/r1_probe_gather.md).
+// records of a fetched line do work instead of 1 (profiles/r1_notes.md §1).
 // A warp owns chunks of 32 groups: lane L draws the block of group L, then in iteration k the warp
 // processes groups k*(32/B).. with B lanes per group reading the B records (coalesced: one line per B
 // lanes); the block base travels by shuffle. One Philox per B events instead of one per event.

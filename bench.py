@@ -17,7 +17,7 @@ per pass; for N>1 the same table is dst-sharded over the ranks (configs[3], stro
              B_alg = 16 B + 16 B * gated fraction; traffic = ncu DRAM bytes (profiles/).
   cpu_baseline : the oracle (host C++ restatement, oracle/oracle_b.cpp) on all host threads, bounded sample.
 --impl reference : the reference ships no CPU traversal and its Metal/AppKit app cannot be built here
-  (DESIGN.md §6); this arm times the oracle port of the reference algorithm on the host cores.
+  (DESIGN.md §3); this arm times the oracle port of the reference algorithm on the host cores.
 """
 from __future__ import annotations
 

@@ -161,7 +161,7 @@ typedef struct abnn_params {
      * process sample_block consecutive table records starting at a Philox-chosen, block-aligned
      * position: edge(i) = B*mulhi64(philox(seed, i - i%B).xy, ceil(n/B)) + i%B  (skipped if >= n).
      * 1 = every event draws its own edge (README.md:77). 8 = one 128-byte HBM line per draw (B200's
-     * DRAM fetch granularity: a random 16-byte gather costs a whole line, profiles/r1_probe_gather.md).
+     * DRAM fetch granularity: a random 16-byte gather costs a whole line, profiles/r1_notes.md §1).
      * Power of two, <= 32. Every edge is still sampled with equal probability. */
     uint32_t sample_block;
     uint32_t table_order;          /* abnn_table_order                                          */
