@@ -69,6 +69,10 @@ struct abnn_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
     cudaEvent_t timer[8]{};
     abnn_synapse* d_syn = nullptr;
+    abnn_synapse* d_spare = nullptr;      // second table (cap records) kept between sorted growth steps when memory allows
+    abnn_synapse* mg_new = nullptr; u32* mg_keys = nullptr; void* mg_tmp = nullptr; u32 mg_cap = 0; size_t mg_tmp_bytes = 0;
+    u32* mg_cnt = nullptr; void* mg_scan = nullptr; size_t mg_scan_bytes = 0;   // sorted-growth scratch (merge_grown)
+    size_t mem_total = 0;
     u64* d_ts = nullptr;
     DevPtrs d{};
     u32 grow_cap = 0, grow_buf = 0;
@@ -303,6 +307,55 @@ int sort_table(abnn_handle* h)
     return 0;
 }
 
+// ABNN_TABLE_DST_SORTED growth: the m candidates list[0..m) (in append order) become records, are sorted by dst
+// (stable) and merged into the sorted table out of place; the tables are then swapped. Scratch lives only here.
+int merge_grown(abnn_handle* h, const GrowCand* list, u32 m)
+{
+    const u64 n = h->n_local;
+    const u32 span = (u32)(h->hi - h->lo);
+    // scratch for the new records is cached in the handle (cudaMalloc / cudaFree next to a 16 GB table cost more
+    // than the merge itself)
+    if (m > h->mg_cap) {
+        cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp);
+        h->mg_new = nullptr; h->mg_keys = nullptr; h->mg_tmp = nullptr; h->mg_cap = 0;
+        const u32 cap_m = next_pow2(m);
+        h->mg_tmp_bytes = sort_by_dst_temp_bytes(cap_m);
+        CU(cudaMalloc(&h->mg_new, 2 * (size_t)cap_m * sizeof(abnn_synapse)));
+        CU(cudaMalloc(&h->mg_keys, 2 * (size_t)cap_m * sizeof(u32)));
+        CU(cudaMalloc(&h->mg_tmp, h->mg_tmp_bytes ? h->mg_tmp_bytes : 16));
+        h->mg_cap = cap_m;
+    }
+    if (!h->mg_cnt) {
+        h->mg_scan_bytes = merge_scan_temp_bytes((u64)span + 1);
+        CU(cudaMalloc(&h->mg_cnt, ((size_t)span + 1) * sizeof(u32)));
+        CU(cudaMalloc(&h->mg_scan, h->mg_scan_bytes ? h->mg_scan_bytes : 16));
+    }
+    abnn_synapse* out = h->d_spare;
+    h->d_spare = nullptr;
+    if (!out) CU(cudaMalloc(&out, h->cap * sizeof(abnn_synapse)));
+    abnn_synapse *nw = h->mg_new, *nw_alt = h->mg_new + h->mg_cap;
+    cudaError_t e = cudaMemsetAsync(h->mg_cnt, 0, ((size_t)span + 1) * sizeof(u32), h->st);
+    if (e == cudaSuccess) e = launch_grow_append(list, m, nw, 0, h->p.w_init, h->st);
+    bool in_alt = false;
+    int nb = 1; while ((1ull << nb) < h->N) ++nb;
+    if (e == cudaSuccess) e = launch_sort_by_dst(nw, nw_alt, h->mg_keys, h->mg_keys + h->mg_cap, m, nb, h->mg_tmp, h->mg_tmp_bytes, &in_alt, h->st);
+    if (e == cudaSuccess) e = launch_merge_sorted(h->d_syn, n, in_alt ? nw_alt : nw, m, (u32)h->lo, span, h->mg_cnt, h->mg_scan,
+                                                  h->mg_scan_bytes, out, h->sm_count, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) {
+        cudaFree(out); cudaGetLastError();
+        return fail(ABNN_ERR_CUDA, std::string("merge_grown: ") + cudaGetErrorString(e));
+    }
+    // the old table becomes the spare of the next growth step (freeing and re-allocating 16 GB costs ~18 ms)
+    // unless two tables would take more than half of the device memory
+    if (2 * h->cap * sizeof(abnn_synapse) <= h->mem_total / 2) h->d_spare = h->d_syn;
+    else cudaFree(h->d_syn);
+    h->d_syn = out; h->d.syn = out;
+    if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old table pointer
+    h->n_local = n + m;
+    return 0;
+}
+
 // EXACT execution: phase 1 (candidates) -> radix sort by (dst, event) -> phase 3 (per-destination chains).
 int run_exact(abnn_handle* h, const KParams& kp)
 {
@@ -448,6 +501,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); h->sm_count = v;
     cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev); h->l2_bytes = (size_t)v;
+    { size_t mem_free = 0; cudaMemGetInfo(&mem_free, &h->mem_total); }
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
@@ -565,7 +619,8 @@ void abnn_destroy(abnn_handle* h)
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->comm) ncclCommDestroy(h->comm);
-    cudaFree(h->d_syn); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
+    cudaFree(h->d_syn); cudaFree(h->d_spare); cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp); cudaFree(h->mg_cnt);
+    cudaFree(h->mg_scan); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
     cudaFree(h->d_vec); cudaFreeHost(h->h_vec);
     cudaFree(h->rs.rate); cudaFree(h->rs.iir); cudaFree(h->rs.fir); cudaFree(h->rs.smooth); cudaFree(h->rs.spikes);
     cudaFree(h->d_stats); cudaFreeHost(h->h_pin); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -1272,10 +1327,15 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
             const u32 owned = (u32)owned64;
             const u64 room = h->cap - h->n_local;
             const u32 m = (u32)std::min<u64>(owned, room);
-            CU(launch_grow_append(list, m, h->d_syn, h->n_local, h->p.w_init, h->st));
-            h->n_local += m;
+            static const bool resort = getenv("ABNN_GROW_RESORT") != nullptr;      // measurements: full radix re-sort instead
+            if (m && h->p.table_order == ABNN_TABLE_DST_SORTED && !resort) {
+                RET(merge_grown(h, list, m));                                        // sorted insert, no re-sort of the table
+            } else {
+                CU(launch_grow_append(list, m, h->d_syn, h->n_local, h->p.w_init, h->st));
+                h->n_local += m;
+                if (m) RET(sort_table(h));
+            }
             s.appended = m; s.dropped = owned - m;
-            if (m) RET(sort_table(h));
         }
         k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
         CU(cudaGetLastError());

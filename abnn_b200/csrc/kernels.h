@@ -64,6 +64,12 @@ size_t sort_by_dst_temp_bytes(u64 n);
 cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, u32* keys_alt, u64 n, int key_bits,
                                void* tmp, size_t tmp_bytes, bool* result_in_alt, cudaStream_t st);
 
+// Stable insertion of m new records (sorted by dst, ties in append order) into the dst-sorted table of n records,
+// out of place: out[0 .. n+m). cnt: dst_span + 1 zeroed u32 slots (per-neuron histogram -> prefix sums).
+size_t merge_scan_temp_bytes(u64 n_slots);
+cudaError_t launch_merge_sorted(const abnn_synapse* syn, u64 n, const abnn_synapse* nw_sorted, u32 m, u32 dst_lo, u32 dst_span,
+                                u32* cnt, void* scan_tmp, size_t scan_tmp_bytes, abnn_synapse* out, int sm_count, cudaStream_t st);
+
 // init.cu
 cudaError_t launch_init_er_beta(abnn_synapse* syn, u64 g0, u64 count, u64 seed, u64 n_neuron, u64 dlo, u64 dhi,
                                 int sm_count, cudaStream_t st);

@@ -10,6 +10,7 @@
 //   * k_grow_*       : growth candidates staged by firing events are ordered by the tick ordinal of
 //                      the event that produced them (bitonic sort) and appended in that order.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -153,6 +154,63 @@ cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, 
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, key_bits, st);
     if (e != cudaSuccess) return e;
     *result_in_alt = v.Current() != reinterpret_cast<uint4*>(syn);
+    return cudaGetLastError();
+}
+
+// ---- ABNN_TABLE_DST_SORTED: insert m new records into the sorted table of n records (stable: behind the
+// existing records of their destination) without re-sorting it. With cnt_less[d] = number of new records
+// whose dst < d (histogram + prefix sum over the neurons, new records sorted by (dst, order)):
+//   existing record i  ->  out[i + cnt_less[dst_i]]                       (one streaming pass, 32 B per record)
+//   new record j       ->  out[upper_bound(existing dst, dst_j) + j]      (m binary searches)
+// Out of place (the caller swaps the tables). 10^9 records: ~11 ms instead of ~70 ms for the radix re-sort.
+__global__ void k_new_hist(const abnn_synapse* nw, u32 m, u32 dst_lo, u32* cnt)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) atomicAdd(&cnt[nw[j].dst - dst_lo + 1], 1u);
+}
+__global__ void __launch_bounds__(256) k_merge_existing(const abnn_synapse* __restrict__ syn, u64 n, u32 dst_lo,
+                                                        const u32* __restrict__ cnt_less, abnn_synapse* __restrict__ out)
+{
+    const uint4* in = reinterpret_cast<const uint4*>(syn);
+    uint4* o = reinterpret_cast<uint4*>(out);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const uint4 r = __ldcs(in + i);
+        __stcs(o + i + cnt_less[r.y - dst_lo], r);
+    }
+}
+__global__ void k_merge_new(const abnn_synapse* __restrict__ syn, u64 n, const abnn_synapse* __restrict__ nw, u32 m,
+                            abnn_synapse* __restrict__ out)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const abnn_synapse r = nw[j];
+    u64 lo = 0, hi = n;                                  // first existing record with dst > r.dst
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (syn[mid].dst <= r.dst) lo = mid + 1; else hi = mid;
+    }
+    out[lo + j] = r;
+}
+size_t merge_scan_temp_bytes(u64 n_slots)
+{
+    size_t b = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, b, (u32*)nullptr, (u32*)nullptr, (long long)n_slots);
+    return b;
+}
+cudaError_t launch_merge_sorted(const abnn_synapse* syn, u64 n, const abnn_synapse* nw_sorted, u32 m, u32 dst_lo, u32 dst_span,
+                                u32* cnt /* dst_span + 1, zeroed */, void* scan_tmp, size_t scan_tmp_bytes, abnn_synapse* out,
+                                int sm_count, cudaStream_t st)
+{
+    if (!m) return cudaSuccess;
+    k_new_hist<<<(m + 255) / 256, 256, 0, st>>>(nw_sorted, m, dst_lo, cnt);
+    cudaError_t e = cub::DeviceScan::InclusiveSum(scan_tmp, scan_tmp_bytes, cnt, cnt, (long long)dst_span + 1, st);
+    if (e != cudaSuccess) return e;
+    if (n) {
+        u64 blocks = (n + 255) / 256;
+        if (blocks > (u64)sm_count * 16) blocks = (u64)sm_count * 16;
+        k_merge_existing<<<(unsigned)blocks, 256, 0, st>>>(syn, n, dst_lo, cnt, out);
+    }
+    k_merge_new<<<(m + 255) / 256, 256, 0, st>>>(syn, n, nw_sorted, m, out);
     return cudaGetLastError();
 }
 

@@ -24,7 +24,10 @@ with Brain(p) as b:
     st = b.run_pass(a.events)                              # fires stage growth candidates
     t0 = time.perf_counter(); ss = b.prune_and_grow(); t_struct = time.perf_counter() - t0
     t0 = time.perf_counter(); s2 = b.prune_and_grow(); t_prune_only = time.perf_counter() - t0   # nothing staged, nothing below w_prune: compaction sweep only
+    st2 = b.run_pass(a.events)
+    t0 = time.perf_counter(); ss3 = b.prune_and_grow(); t_struct2 = time.perf_counter() - t0     # steady state: spare table already allocated
     print(json.dumps({"n_syn": a.syn, "init_and_sort_s": t_init, "pass_fired": st.fired, "grown_staged": st.grown,
                       "pruned": ss.pruned, "appended": ss.appended, "dropped": ss.dropped, "n_after": ss.n_after,
-                      "prune_grow_resort_ms": 1e3 * t_struct, "compaction_sweep_ms": 1e3 * t_prune_only,
+                      "first_structural_step_ms": 1e3 * t_struct, "steady_structural_step_ms": 1e3 * t_struct2,
+                      "steady_pruned": ss3.pruned, "steady_appended": ss3.appended, "compaction_sweep_ms": 1e3 * t_prune_only,
                       "compaction_sweep_GBps": 32.0 * ss.n_after / t_prune_only / 1e9}))
