@@ -1,8 +1,8 @@
 // abnn_b200/csrc/structural.cu — structural plasticity (README.md:120-127; absent from the reference
 // code) as deterministic, scan-based stream operations:
 //   * k_compact      : STABLE stream compaction of the synapse table in ONE pass over HBM
-//                      (16 B read per record + 16 B write per kept record), single-pass chained scan
-//                      with decoupled look-back. Works in place: a tile publishes its count only
+//                      (16 B read per record + 16 B write per kept record, both coalesced), single-pass
+//                      chained scan with decoupled look-back. Works in place: a tile publishes its count only
 //                      after its records are in registers, and a tile's destination range never
 //                      reaches past its own source range, so no unread record is overwritten.
 //                      Used for pruning (keep !(w < w_prune)) and for the dst-owner filter of
@@ -41,27 +41,29 @@ __global__ void __launch_bounds__(CT) k_compact(const CompactArgs a, u32* ticket
     __syncthreads();
     const u32 tile = s_tile;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u64 base = (u64)tile * TILE + (u64)threadIdx.x * CI;
+    // a warp owns 32 * CI consecutive records; lane l loads records l, l + 32, ... (coalesced 512-byte rows).
+    // Stable rank inside the warp: rows before mine (popc of their keep ballots) + kept lanes before me in my row.
+    const u64 wbase = (u64)tile * TILE + (u64)warp * (32 * CI);
     const uint4* in = reinterpret_cast<const uint4*>(a.in);
     uint4 rec[CI];
-    u32 keep = 0, cnt = 0;
+    unsigned bal[CI];
+    u32 warp_total = 0;
 #pragma unroll
     for (int j = 0; j < CI; ++j) {
-        if (base + j < a.n) {
-            rec[j] = in[base + j];
-            if (keep_record(a, rec[j])) { keep |= 1u << j; ++cnt; }
+        const u64 idx = wbase + (u64)j * 32 + lane;
+        bool k = false;
+        if (idx < a.n) {
+            rec[j] = in[idx];
+            k = keep_record(a, rec[j]);
         }
+        bal[j] = __ballot_sync(0xffffffffu, k);
+        warp_total += __popc(bal[j]);
     }
-    // block-wide exclusive scan of cnt
-    u32 inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 0) s_warp[warp] = warp_total;
     __syncthreads();
     u32 warp_off = 0, block_total = 0;
 #pragma unroll
     for (int w = 0; w < CT / 32; ++w) { const u32 v = s_warp[w]; if (w < (int)warp) warp_off += v; block_total += v; }
-    const u32 excl = warp_off + inc - cnt;
 
     // chained scan across tiles: warp 0 looks back 32 predecessors at a time
     if (warp == 0) {
@@ -101,10 +103,13 @@ __global__ void __launch_bounds__(CT) k_compact(const CompactArgs a, u32* ticket
     }
     __syncthreads();
     uint4* out = reinterpret_cast<uint4*>(a.out);
-    u64 pos = s_prefix + excl;
+    u64 pos = s_prefix + warp_off;
+    const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int j = 0; j < CI; ++j)
-        if (keep & (1u << j)) { if (pos < a.out_cap) out[pos] = rec[j]; ++pos; }
+    for (int j = 0; j < CI; ++j) {
+        if ((bal[j] >> lane) & 1u) { const u64 p = pos + __popc(bal[j] & lt); if (p < a.out_cap) out[p] = rec[j]; }
+        pos += __popc(bal[j]);
+    }
 }
 
 size_t compact_scratch_bytes(u64 n)
