@@ -72,6 +72,7 @@ struct abnn_handle {
     abnn_synapse* d_spare = nullptr;      // second table (cap records) kept between sorted growth steps when memory allows
     abnn_synapse* mg_new = nullptr; u32* mg_keys = nullptr; void* mg_tmp = nullptr; u32 mg_cap = 0; size_t mg_tmp_bytes = 0;
     u32* mg_cnt = nullptr; void* mg_scan = nullptr; size_t mg_scan_bytes = 0;   // sorted-growth scratch (merge_grown)
+    u32* mg_pruned = nullptr;                                                   // per-neuron removed counts (fused prune + merge)
     size_t mem_total = 0;
     u64* d_ts = nullptr;
     DevPtrs d{};
@@ -309,7 +310,10 @@ int sort_table(abnn_handle* h)
 
 // ABNN_TABLE_DST_SORTED growth: the m candidates list[0..m) (in append order) become records, are sorted by dst
 // (stable) and merged into the sorted table out of place; the tables are then swapped. Scratch lives only here.
-int merge_grown(abnn_handle* h, const GrowCand* list, u32 m)
+// Sorted insertion of the first m growth candidates of `list` into the dst-sorted table. With kept_out != null the
+// pruning (w < w_prune) happens in the same pass over the table (launch_prune_merge_sorted) and *kept_out receives the
+// number of existing records that survived.
+int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nullptr)
 {
     const u64 n = h->n_local;
     const u32 span = (u32)(h->hi - h->lo);
@@ -326,9 +330,13 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m)
         h->mg_cap = cap_m;
     }
     if (!h->mg_cnt) {
-        h->mg_scan_bytes = merge_scan_temp_bytes((u64)span + 1);
+        h->mg_scan_bytes = merge_scan_temp_bytes((u64)span + 2);
         CU(cudaMalloc(&h->mg_cnt, ((size_t)span + 1) * sizeof(u32)));
         CU(cudaMalloc(&h->mg_scan, h->mg_scan_bytes ? h->mg_scan_bytes : 16));
+    }
+    if (kept_out) {
+        if (!h->mg_pruned) CU(cudaMalloc(&h->mg_pruned, ((size_t)span + 2) * sizeof(u32)));
+        RET(ensure_scratch(h, compact_scratch_bytes(n)));
     }
     abnn_synapse* out = h->d_spare;
     h->d_spare = nullptr;
@@ -339,8 +347,17 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m)
     bool in_alt = false;
     int nb = 1; while ((1ull << nb) < h->N) ++nb;
     if (e == cudaSuccess) e = launch_sort_by_dst(nw, nw_alt, h->mg_keys, h->mg_keys + h->mg_cap, m, nb, h->mg_tmp, h->mg_tmp_bytes, &in_alt, h->st);
-    if (e == cudaSuccess) e = launch_merge_sorted(h->d_syn, n, in_alt ? nw_alt : nw, m, (u32)h->lo, span, h->mg_cnt, h->mg_scan,
-                                                  h->mg_scan_bytes, out, h->sm_count, h->st);
+    u64 kept = n;
+    if (kept_out) {
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->mg_pruned, 0, ((size_t)span + 2) * sizeof(u32), h->st);
+        if (e == cudaSuccess) e = launch_prune_merge_sorted(h->d_syn, n, h->p.w_prune, in_alt ? nw_alt : nw, m, (u32)h->lo, span, h->mg_cnt,
+                                                            h->mg_pruned, h->mg_scan, h->mg_scan_bytes, h->d_scratch, h->d_total, out,
+                                                            h->cap, h->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st);
+    } else if (e == cudaSuccess) {
+        e = launch_merge_sorted(h->d_syn, n, in_alt ? nw_alt : nw, m, (u32)h->lo, span, h->mg_cnt, h->mg_scan, h->mg_scan_bytes, out,
+                                h->sm_count, h->st);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     if (e != cudaSuccess) {
         cudaFree(out); cudaGetLastError();
@@ -352,7 +369,8 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m)
     else cudaFree(h->d_syn);
     h->d_syn = out; h->d.syn = out;
     if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old table pointer
-    h->n_local = n + m;
+    h->n_local = kept + m;
+    if (kept_out) *kept_out = kept;
     return 0;
 }
 
@@ -620,7 +638,7 @@ void abnn_destroy(abnn_handle* h)
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_syn); cudaFree(h->d_spare); cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp); cudaFree(h->mg_cnt);
-    cudaFree(h->mg_scan); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
+    cudaFree(h->mg_pruned); cudaFree(h->mg_scan); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
     cudaFree(h->d_vec); cudaFreeHost(h->h_vec);
     cudaFree(h->rs.rate); cudaFree(h->rs.iir); cudaFree(h->rs.fir); cudaFree(h->rs.smooth); cudaFree(h->rs.spikes);
     cudaFree(h->d_stats); cudaFreeHost(h->h_pin); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -1264,70 +1282,95 @@ int abnn_get_loss(abnn_handle* h, double* last_loss, uint64_t* windows_done)
 }
 
 // ---- structural plasticity ------------------------------------------------------------------------
+namespace {
+// Growth candidates staged since the last structural step, from every rank, sorted by the tick ordinal of the firing
+// event; *owned = how many of them target this rank's neurons (they sort first). Collective when world_size > 1.
+int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out)
+{
+    *list_out = h->d.grow; *owned_out = 0;
+    DevScalars sc; RET(read_scalars(h, &sc));
+    if (sc.grow_overflow) {
+        k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
+        return fail(ABNN_ERR_CAPACITY, "growth staging buffer overflowed; call abnn_prune_and_grow more often");
+    }
+    u32 n = sc.grow_count;
+    GrowCand* list = h->d.grow;
+    u32 total = n;
+    if (h->p.world_size > 1) {
+        if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
+        // every rank needs everyone's candidates: exchange counts, pad to the maximum, allgather
+        u64 mine = n;
+        CU(cudaMemcpyAsync(h->d_counts + h->p.rank, &mine, sizeof(u64), cudaMemcpyHostToDevice, h->st));
+        NC(ncclAllGather(h->d_counts + h->p.rank, h->d_counts, 1, ncclUint64, h->comm, h->st));
+        std::vector<u64> cnt(h->p.world_size);
+        CU(cudaMemcpyAsync(cnt.data(), h->d_counts, sizeof(u64) * h->p.world_size, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        u32 maxc = 0;
+        for (u64 c : cnt) maxc = std::max<u32>(maxc, (u32)c);
+        total = maxc * h->p.world_size;
+        const u32 need = next_pow2(std::max<u32>(total, 1));
+        if (need > h->grow_all_buf) {
+            if (h->d_grow_all) CU(cudaFree(h->d_grow_all));
+            h->d_grow_all = nullptr;
+            CU(cudaMalloc(&h->d_grow_all, (size_t)need * sizeof(GrowCand)));
+            h->grow_all_buf = need;
+        }
+        if (maxc) {
+            if (maxc > n) { k_pad_grow<<<(maxc - n + 255) / 256, 256, 0, h->st>>>(h->d.grow, n, maxc); CU(cudaGetLastError()); }
+            NC(ncclAllGather(h->d.grow, h->d_grow_all, (size_t)maxc * sizeof(GrowCand), ncclUint8, h->comm, h->st));
+        }
+        list = h->d_grow_all;
+    }
+    if (total) {
+        const u32 np2 = next_pow2(total);
+        CU(cudaMemsetAsync(h->d_total + 1, 0, sizeof(u64), h->st));
+        CU(launch_grow_sort_count(list, total, np2, (u32)h->lo, (u32)h->hi, reinterpret_cast<u32*>(h->d_total + 1), h->st));
+        u64 owned64 = 0;
+        CU(cudaMemcpyAsync(&owned64, h->d_total + 1, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        *owned_out = (u32)owned64;
+    }
+    *list_out = list;
+    return 0;
+}
+}  // namespace
+
 int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
 {
     RET(use(h));
     abnn_structural_stats s{};
     s.n_before = h->n_local;
-    // 1. prune: stable in-place compaction
-    if (h->p.w_prune > 0.f && h->n_local) {
-        CompactArgs a{};
-        a.in = h->d_syn; a.out = h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
-        a.out_cap = h->cap;
-        RET(ensure_scratch(h, compact_scratch_bytes(a.n)));
-        CU(launch_compact(a, h->d_scratch, h->d_total, h->st));
+    const bool prune = h->p.w_prune > 0.f && h->n_local, grow = h->p.p_new > 0.f;
+    static const bool resort = getenv("ABNN_GROW_RESORT") != nullptr;      // measurements: full radix re-sort instead of the merge
+    static const bool no_fuse = getenv("ABNN_NO_FUSED_PRUNE") != nullptr;  // measurements: prune and merge as two passes
+    // growth candidates first (they do not depend on the table): their number decides how the table is rewritten
+    GrowCand* list = nullptr;
+    u32 owned = 0;
+    if (grow) RET(gather_growth(h, &list, &owned));
+    if (prune && owned && h->p.table_order == ABNN_TABLE_DST_SORTED && !resort && !no_fuse && owned <= h->cap - h->n_local) {
+        // 1+2 fused: one pass over the table removes the pruned records and opens the slots of the new ones
         u64 kept = 0;
-        CU(cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
-        CU(cudaStreamSynchronize(h->st));
-        s.pruned = h->n_local - kept;
-        h->n_local = kept;
-    }
-    // 2. grow: candidates in event order
-    if (h->p.p_new > 0.f) {
-        DevScalars sc; RET(read_scalars(h, &sc));
-        if (sc.grow_overflow) {
-            k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
-            return fail(ABNN_ERR_CAPACITY, "growth staging buffer overflowed; call abnn_prune_and_grow more often");
-        }
-        u32 n = sc.grow_count;
-        GrowCand* list = h->d.grow;
-        u32 total = n;
-        if (h->p.world_size > 1) {
-            if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
-            // every rank needs everyone's candidates: exchange counts, pad to the maximum, allgather
-            u64 mine = n;
-            CU(cudaMemcpyAsync(h->d_counts + h->p.rank, &mine, sizeof(u64), cudaMemcpyHostToDevice, h->st));
-            NC(ncclAllGather(h->d_counts + h->p.rank, h->d_counts, 1, ncclUint64, h->comm, h->st));
-            std::vector<u64> cnt(h->p.world_size);
-            CU(cudaMemcpyAsync(cnt.data(), h->d_counts, sizeof(u64) * h->p.world_size, cudaMemcpyDeviceToHost, h->st));
+        RET(merge_grown(h, list, owned, &kept));
+        s.pruned = s.n_before - kept;
+        s.appended = owned;
+    } else {
+        // 1. prune: stable in-place compaction
+        if (prune) {
+            CompactArgs a{};
+            a.in = h->d_syn; a.out = h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
+            a.out_cap = h->cap;
+            RET(ensure_scratch(h, compact_scratch_bytes(a.n)));
+            CU(launch_compact(a, h->d_scratch, h->d_total, h->st));
+            u64 kept = 0;
+            CU(cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
             CU(cudaStreamSynchronize(h->st));
-            u32 maxc = 0;
-            for (u64 c : cnt) maxc = std::max<u32>(maxc, (u32)c);
-            total = maxc * h->p.world_size;
-            const u32 need = next_pow2(std::max<u32>(total, 1));
-            if (need > h->grow_all_buf) {
-                if (h->d_grow_all) CU(cudaFree(h->d_grow_all));
-                h->d_grow_all = nullptr;
-                CU(cudaMalloc(&h->d_grow_all, (size_t)need * sizeof(GrowCand)));
-                h->grow_all_buf = need;
-            }
-            if (maxc) {
-                if (maxc > n) { k_pad_grow<<<(maxc - n + 255) / 256, 256, 0, h->st>>>(h->d.grow, n, maxc); CU(cudaGetLastError()); }
-                NC(ncclAllGather(h->d.grow, h->d_grow_all, (size_t)maxc * sizeof(GrowCand), ncclUint8, h->comm, h->st));
-            }
-            list = h->d_grow_all;
+            s.pruned = h->n_local - kept;
+            h->n_local = kept;
         }
-        if (total) {
-            const u32 np2 = next_pow2(total);
-            CU(cudaMemsetAsync(h->d_total + 1, 0, sizeof(u64), h->st));
-            CU(launch_grow_sort_count(list, total, np2, (u32)h->lo, (u32)h->hi, reinterpret_cast<u32*>(h->d_total + 1), h->st));
-            u64 owned64 = 0;
-            CU(cudaMemcpyAsync(&owned64, h->d_total + 1, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
-            CU(cudaStreamSynchronize(h->st));
-            const u32 owned = (u32)owned64;
+        // 2. grow: candidates in event order, as many as fit
+        if (owned) {
             const u64 room = h->cap - h->n_local;
             const u32 m = (u32)std::min<u64>(owned, room);
-            static const bool resort = getenv("ABNN_GROW_RESORT") != nullptr;      // measurements: full radix re-sort instead
             if (m && h->p.table_order == ABNN_TABLE_DST_SORTED && !resort) {
                 RET(merge_grown(h, list, m));                                        // sorted insert, no re-sort of the table
             } else {
@@ -1337,6 +1380,8 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
             }
             s.appended = m; s.dropped = owned - m;
         }
+    }
+    if (grow) {
         k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
         CU(cudaGetLastError());
     }

@@ -48,6 +48,11 @@ struct CompactArgs {
     u32 pred;
     float w_prune;
     u32 dst_lo, dst_hi;
+    // fused prune + sorted merge (launch_prune_merge_sorted; out of place only): a kept record lands shift[dst - shift_lo]
+    // slots behind its stable rank, a removed one is counted in drop_hist[dst - shift_lo + 1]. Null = plain compaction.
+    const u32* shift;
+    u32 shift_lo;
+    u32* drop_hist;
 };
 size_t compact_scratch_bytes(u64 n);
 // Stable stream compaction (single pass, decoupled look-back). Kept count lands in *d_total.
@@ -69,6 +74,12 @@ cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, 
 size_t merge_scan_temp_bytes(u64 n_slots);
 cudaError_t launch_merge_sorted(const abnn_synapse* syn, u64 n, const abnn_synapse* nw_sorted, u32 m, u32 dst_lo, u32 dst_span,
                                 u32* cnt, void* scan_tmp, size_t scan_tmp_bytes, abnn_synapse* out, int sm_count, cudaStream_t st);
+
+// Pruning (w < w_prune) and the sorted insertion above in one pass over the table; pruned: dst_span + 2 zeroed u32 slots,
+// scan_tmp sized for dst_span + 2 slots, compact_scratch = compact_scratch_bytes(n). Kept count lands in *d_total.
+cudaError_t launch_prune_merge_sorted(const abnn_synapse* syn, u64 n, float w_prune, const abnn_synapse* nw_sorted, u32 m, u32 dst_lo,
+                                      u32 dst_span, u32* cnt, u32* pruned, void* scan_tmp, size_t scan_tmp_bytes,
+                                      void* compact_scratch, u64* d_total, abnn_synapse* out, u64 out_cap, cudaStream_t st);
 
 // init.cu
 cudaError_t launch_init_er_beta(abnn_synapse* syn, u64 g0, u64 count, u64 seed, u64 n_neuron, u64 dlo, u64 dhi,

@@ -9,6 +9,8 @@
 //                      abnn_upload_synapses.
 //   * k_grow_*       : growth candidates staged by firing events are ordered by the tick ordinal of
 //                      the event that produced them (bitonic sort) and appended in that order.
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -32,6 +34,9 @@ __device__ __forceinline__ bool keep_record(const CompactArgs& a, const uint4& r
 }
 }  // namespace
 
+// Measured and reverted (profiles/r1_notes.md §7): persistent CTAs with the next ticket requested early and 4 CTAs per SM
+// (sweep of 9.3e8 records 24.7 ms instead of 11.6 ms), and a look-back window of 8 x 32 descriptors per round trip
+// (16.7 ms): the single-pass chained scan below is the fastest of the three.
 __global__ void __launch_bounds__(CT) k_compact(const CompactArgs a, u32* ticket, volatile u64* desc, u64* total)
 {
     __shared__ u32 s_tile;
@@ -58,6 +63,16 @@ __global__ void __launch_bounds__(CT) k_compact(const CompactArgs a, u32* ticket
         }
         bal[j] = __ballot_sync(0xffffffffu, k);
         warp_total += __popc(bal[j]);
+        if (a.drop_hist) {                                   // fused prune + merge: removed records per neuron
+            // one atomic per destination and row: in a dst-sorted table the removed records of a row share one or two
+            // destinations, and per-record atomics on one address serialise (measured: 71M removals took 250 ms)
+            const bool drop = idx < a.n && !k;
+            const unsigned dm = __ballot_sync(0xffffffffu, drop);
+            if (drop) {
+                const unsigned peers = __match_any_sync(dm, rec[j].y);
+                if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&a.drop_hist[rec[j].y - a.shift_lo + 1], (u32)__popc(peers));
+            }
+        }
     }
     if (lane == 0) s_warp[warp] = warp_total;
     __syncthreads();
@@ -107,7 +122,11 @@ __global__ void __launch_bounds__(CT) k_compact(const CompactArgs a, u32* ticket
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < CI; ++j) {
-        if ((bal[j] >> lane) & 1u) { const u64 p = pos + __popc(bal[j] & lt); if (p < a.out_cap) out[p] = rec[j]; }
+        if ((bal[j] >> lane) & 1u) {
+            u64 p = pos + __popc(bal[j] & lt);
+            if (a.shift) p += a.shift[rec[j].y - a.shift_lo];           // fused prune + merge: room for the new records in front
+            if (p < a.out_cap) out[p] = rec[j];
+        }
         pos += __popc(bal[j]);
     }
 }
@@ -196,6 +215,22 @@ __global__ void k_merge_new(const abnn_synapse* __restrict__ syn, u64 n, const a
     }
     out[lo + j] = r;
 }
+// Fused prune + merge: the existing table `syn` is the one BEFORE pruning; pruned_le[h + 1] = removed records with
+// dst <= dst_lo + h (inclusive scan of the histogram k_compact filled), so upper_bound(syn, dst) - pruned_le is the
+// number of KEPT existing records up to and including that destination.
+__global__ void k_merge_new_pruned(const abnn_synapse* __restrict__ syn, u64 n, const abnn_synapse* __restrict__ nw, u32 m,
+                                   u32 dst_lo, const u32* __restrict__ pruned_le, abnn_synapse* __restrict__ out)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const abnn_synapse r = nw[j];
+    u64 lo = 0, hi = n;                                  // first existing record with dst > r.dst
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (syn[mid].dst <= r.dst) lo = mid + 1; else hi = mid;
+    }
+    out[lo - pruned_le[r.dst - dst_lo + 1] + j] = r;
+}
 size_t merge_scan_temp_bytes(u64 n_slots)
 {
     size_t b = 0;
@@ -216,6 +251,29 @@ cudaError_t launch_merge_sorted(const abnn_synapse* syn, u64 n, const abnn_synap
         k_merge_existing<<<(unsigned)blocks, 256, 0, st>>>(syn, n, dst_lo, cnt, out);
     }
     k_merge_new<<<(m + 255) / 256, 256, 0, st>>>(syn, n, nw_sorted, m, out);
+    return cudaGetLastError();
+}
+
+// Prune and sorted insertion in ONE pass over the table (out of place): kept record with stable rank p goes to
+// out[p + cnt_less[dst]], new record j to out[kept records with dst <= dst_j + j]. Same table, bit for bit, as
+// launch_compact (in place) followed by launch_merge_sorted, with half the HBM traffic (16 B read + 16 B written per
+// record instead of twice that). Kept count lands in *d_total.
+cudaError_t launch_prune_merge_sorted(const abnn_synapse* syn, u64 n, float w_prune, const abnn_synapse* nw_sorted, u32 m, u32 dst_lo,
+                                      u32 dst_span, u32* cnt /* dst_span + 1, zeroed */, u32* pruned /* dst_span + 2, zeroed */,
+                                      void* scan_tmp, size_t scan_tmp_bytes, void* compact_scratch, u64* d_total,
+                                      abnn_synapse* out, u64 out_cap, cudaStream_t st)
+{
+    k_new_hist<<<(m + 255) / 256, 256, 0, st>>>(nw_sorted, m, dst_lo, cnt);
+    cudaError_t e = cub::DeviceScan::InclusiveSum(scan_tmp, scan_tmp_bytes, cnt, cnt, (long long)dst_span + 1, st);
+    if (e != cudaSuccess) return e;
+    CompactArgs a{};
+    a.in = syn; a.out = out; a.n = n; a.out_cap = out_cap; a.pred = KEEP_NOT_PRUNED; a.w_prune = w_prune;
+    a.shift = cnt; a.shift_lo = dst_lo; a.drop_hist = pruned;
+    e = launch_compact(a, compact_scratch, d_total, st);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceScan::InclusiveSum(scan_tmp, scan_tmp_bytes, pruned, pruned, (long long)dst_span + 2, st);
+    if (e != cudaSuccess) return e;
+    k_merge_new_pruned<<<(m + 255) / 256, 256, 0, st>>>(syn, n, nw_sorted, m, dst_lo, pruned, out);
     return cudaGetLastError();
 }
 

@@ -477,6 +477,37 @@ def test_prune_compaction_is_stable_and_matches_oracle():
     assert sb2.pruned == 0 and b.download_synapses().tobytes() == got.tobytes()
 
 
+def test_structural_step_every_pass_fused_prune_merge_bit_exact():
+    """BASELINE configs[4] regime: pruning + synaptogenesis after EVERY pass on a dst-sorted table. With room for every
+    owned candidate the device removes the pruned records and inserts the new ones in ONE pass over the table
+    (launch_prune_merge_sorted); the table, the counts and everything downstream must equal the oracle's sequential
+    prune -> ordered insert bit for bit, including a pass with nothing to prune and one with nothing to grow."""
+    rng = np.random.default_rng(77)
+    N, n = 20_000, 800_003
+    syn = random_graph(rng, n, N, 0.15, 1.0, dst_lo=32)
+    pre = rng.integers(1, 60_000, N).astype(np.uint64)
+    over = dict(n_input=32, n_output=32, n_hidden=N - 64, n_syn=n, exec_mode=capi.EXEC_EXACT, sample_block=8,
+                table_order=capi.TABLE_DST_SORTED, window_pre=400_000, refractory=20_000, p_new=0.2, w_prune=0.16,
+                w_init=0.17, syn_capacity=n + 200_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(pre, None); x.clock = 60_000; x.set_reward(0.1)
+    grown = pruned = 0
+    for p in range(5):
+        sb, so = b.run_pass(200_003), o.run_pass(200_003)
+        assert_same_stats(sb, so, f"pass {p}")
+        ssb, sso = b.prune_and_grow(), o.prune_and_grow()
+        assert (ssb.n_before, ssb.pruned, ssb.appended, ssb.dropped, ssb.n_after) == \
+               (sso.n_before, sso.pruned, sso.appended, sso.dropped, sso.n_after), f"structural step {p}"
+        assert sso.dropped == 0 and sso.n_after <= n + 200_000       # every candidate fitted: the fused path ran
+        grown += sso.appended; pruned += sso.pruned
+        assert b.download_synapses().tobytes() == o.download_synapses().tobytes(), f"table after structural step {p}"
+    assert grown > 1000 and pruned > 1000
+    sb, so = b.prune_and_grow(), o.prune_and_grow()                   # nothing staged: prune-only path, in place
+    assert (sb.pruned, sb.appended) == (so.pruned, so.appended) and so.appended == 0
+    assert_same_state(b, o)
+
+
 def test_engine_loop_matches_oracle_per_pass_clock():
     """BrainEngine.run_one_pass order of operations (brain-engine.cpp:108-190) in the reference's own
     PER_PASS clock with SERIAL execution, 30 passes: filtered read-out bit-exact every pass."""
