@@ -4,6 +4,19 @@ import csv, io, subprocess, sys
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
         "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        # SURVEY.md §8d evidence list: L2 sectors by operation, hit/miss, persisting (evict_last) vs normal lines, atomics
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_read_evict_last_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_evict_last_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_read_evict_normal_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_evict_normal_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sectors_srcunit_tex_op_write_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_write_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_atom_dot_alu_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_atom_dot_alu_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_atom_evict_last_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_atom_evict_last_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_ltcfabric.sum",
+        "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_atom.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "smsp__inst_executed_op_global_atom.sum", "smsp__inst_executed_op_global_red.sum", "smsp__issue_active.avg.per_cycle_active",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",

@@ -1,6 +1,11 @@
 # A/B measurements on one B200 (scratch script for gpurun; results land in gpurun_out/)
 set -x
-timeout 200 python tools/bench_structural.py > gpurun_out/structural_fused4.json 2> gpurun_out/structural_fused4.err; cat gpurun_out/structural_fused4.json
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_compact --launch-skip 1 --launch-count 2 \
-  -o gpurun_out/prof_compact -f python tools/bench_structural.py > gpurun_out/ncu_compact.log 2>&1
-tail -2 gpurun_out/ncu_compact.log
+run() {  # name, extra bench args
+  name=$1; shift
+  timeout 200 python bench.py --steps 20 --warmup 3 --skip-cpu "$@" > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  python tools/bench_line.py $name < gpurun_out/ab_$name.json
+}
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+ABNN_B200_LIB=variants/lib_v9.so run v9b
+run vis32
+ABNN_L2_ARRAYS=3 run vis32_w80
