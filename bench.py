@@ -81,50 +81,107 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (10 ms period) that is
+    started before the warm-up, so that even a 60 ms timed region (8 GPUs, 200 steps) holds samples; only the samples
+    between mark_start() and mark_stop() are reported. Falls back to `nvidia-smi -lms` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.rows, self.p = index, [], None
+    def __init__(self, index, period_s=0.01):
+        self.index, self.period = index, period_s
+        self.rows = []                      # (perf_counter time, sm MHz, max sm MHz, set of reasons)
+        self.p = self.t = self.nv = None
+        self.t0 = self.t1 = None
+        self.halt = threading.Event()
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            # nvmlClocksEventReason* bit values (nvml.h)
+            self.bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.p = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.halt.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                self.rows.append((time.perf_counter(), sm, self.mx, {n for n, b in self.bits.items() if mask & b}))
+            except Exception:
+                pass
+            self.halt.wait(self.period)
 
-    def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _read_smi(self):
+        for line in self.p.stdout:
+            r = [c.strip() for c in line.split(",")]
             if len(r) < 9:
                 continue
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
+                                  {n for n, v in zip(self.NAMES, r[5:9]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for name, val in zip(names, r[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.t1 is None:
+            self.mark_stop()
+        self.halt.set()
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        if self.t:
+            self.t.join(timeout=2)
+        if not self.p and not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        return self.summarise(self.rows, self.t0, self.t1, "nvml" if self.nv else "nvidia-smi")
+
+    @staticmethod
+    def summarise(rows, t0, t1, source):
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": source}
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        note = None
+        if not inside:                      # timed region shorter than the sampling period: the sample closest to it
+            mid = 0.5 * ((t0 if t0 is not None else rows[0][0]) + t1)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            note = "no sample fell inside the timed region; nearest sample, %.0f ms away" % (1e3 * abs(inside[0][0] - mid))
+        reasons = set()
+        for r in inside:
+            reasons |= r[3]
+        out = {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+               "reasons": sorted(reasons), "samples": len(inside), "source": source}
+        if note:
+            out["note"] = note
+        return out
 
 
 def stimulus_frames(n):
@@ -164,6 +221,9 @@ def warm_timestamps(n_neuron, frac, events, seed=7):
     return lf, start
 
 
+ONE_THREAD = {}     # filled by run_cpu: single-thread rate of the same port
+
+
 def run_cpu(args, steps, warmup, as_reference):
     """Oracle port on all host threads: T dst-shards, one thread each (same partition as multi-GPU)."""
     from abnn_b200 import capi
@@ -194,6 +254,11 @@ def run_cpu(args, steps, warmup, as_reference):
             times.append(dt); gated += st.gated
     ms = 1e3 * float(np.mean(times))
     val = events / (ms * 1e-3)
+    # the 1-thread figure SURVEY.md §8d asks for: shard 0 alone executes its share of one more pass
+    t0 = time.perf_counter()
+    st1 = world.shards[0].run_pass(events)
+    ONE_THREAD["value"] = st1.events / (time.perf_counter() - t0)
+    ONE_THREAD["sample"] = f"{st1.events:,} events of shard 0 ({syn // T:,} synapses), one thread"
     sample = (f"{steps} passes x {events:,} events on a {syn:,}-synapse / {n_neuron:,}-neuron ER-Beta graph "
               f"(same per-event work, table {syn * 16 / 1e9:.1f} GB instead of {args.syn * 16 / 1e9:.1f} GB), "
               f"{T} dst-shards on {T} threads")
@@ -221,7 +286,7 @@ def main():
                        "exec_mode": "serial per dst-shard (oracle), one shard per host thread", "clock": "per_event",
                        "graph": "ER endpoints, Beta(2,8) weights (Philox)", "window_pre_passes": 5, "refractory_passes": 2,
                        "warm_fraction": args.warm_frac, "track_visits": not args.no_visits, "l2": "inputs larger than L2"},
-            "cpu_baseline": {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample, "one_thread": dict(ONE_THREAD),
                              "gated_fraction": g},
             "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference has no CPU traversal and its Metal app cannot be built on Linux; this is the oracle port of its algorithm"}))
@@ -270,17 +335,21 @@ def main():
         b.engine_step(pin_in[it], pin_ex[it], 1000.0, float(it & 1), args.events)
 
     # ---- value: device-timed, K steps ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)       # polls from before the warm-up; reports the samples of the timed region
+    if rank == 0:
+        sampler.start()
     for it in range(W):
         step_device(it)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark_start()
     b.timer_mark(0)
     for it in range(W, W + K):
         step_device(it)
     b.timer_mark(1)
     barrier()
+    if rank == 0:
+        sampler.mark_stop()
     ms_total = b.timer_elapsed(0, 1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -370,7 +439,7 @@ def main():
         }
         if world == 1 and not args.skip_cpu:
             val, ms, T, sample, gc = run_cpu(args, 3, 1, False)
-            line["cpu_baseline"] = {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample,
+            line["cpu_baseline"] = {"value": val, "unit": "events/s", "cores": T, "kind": "port", "sample": sample, "one_thread": dict(ONE_THREAD),
                                     "gated_fraction": gc}
         print(json.dumps(line))
     b.close()
