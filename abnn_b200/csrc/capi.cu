@@ -336,7 +336,7 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nul
     }
     if (kept_out) {
         if (!h->mg_pruned) CU(cudaMalloc(&h->mg_pruned, ((size_t)span + 2) * sizeof(u32)));
-        RET(ensure_scratch(h, compact_scratch_bytes(n)));
+        RET(ensure_scratch(h, std::max(compact_scratch_bytes(n), compact2_scratch_bytes(n))));
     }
     abnn_synapse* out = h->d_spare;
     h->d_spare = nullptr;
@@ -1354,16 +1354,37 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
         s.pruned = s.n_before - kept;
         s.appended = owned;
     } else {
-        // 1. prune: stable in-place compaction
+        // 1. prune: stable compaction — into the spare table (count pass + scatter pass, no chained scan) when there is
+        //    memory for one, else in place (k_compact)
         if (prune) {
+            static const bool in_place_only = getenv("ABNN_PRUNE_IN_PLACE") != nullptr;   // measurements only
+            const bool two_tables = 2 * h->cap * sizeof(abnn_synapse) <= h->mem_total / 2;
+            abnn_synapse* spare = nullptr;
+            if (!in_place_only && (h->d_spare || two_tables)) {
+                spare = h->d_spare; h->d_spare = nullptr;
+                if (!spare && cudaMalloc(&spare, h->cap * sizeof(abnn_synapse)) != cudaSuccess) { cudaGetLastError(); spare = nullptr; }
+            }
             CompactArgs a{};
-            a.in = h->d_syn; a.out = h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
+            a.in = h->d_syn; a.out = spare ? spare : h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
             a.out_cap = h->cap;
-            RET(ensure_scratch(h, compact_scratch_bytes(a.n)));
-            CU(launch_compact(a, h->d_scratch, h->d_total, h->st));
             u64 kept = 0;
-            CU(cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
-            CU(cudaStreamSynchronize(h->st));
+            cudaError_t e = cudaSuccess;
+            int rc = ensure_scratch(h, spare ? compact2_scratch_bytes(a.n) : compact_scratch_bytes(a.n));
+            if (!rc) {
+                e = spare ? launch_compact_two_pass(a, h->d_scratch, h->d_total, h->st) : launch_compact(a, h->d_scratch, h->d_total, h->st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+            }
+            if (rc || e != cudaSuccess) {
+                if (spare) h->d_spare = spare;               // the table itself is untouched when the copy went elsewhere
+                if (rc) return rc;
+                return fail(ABNN_ERR_CUDA, std::string("prune: ") + cudaGetErrorString(e));
+            }
+            if (spare) {                                     // the old table becomes the spare of the next structural step
+                h->d_spare = h->d_syn;
+                h->d_syn = spare; h->d.syn = spare;
+                if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old pointer
+            }
             s.pruned = h->n_local - kept;
             h->n_local = kept;
         }

@@ -57,6 +57,9 @@ struct CompactArgs {
 size_t compact_scratch_bytes(u64 n);
 // Stable stream compaction (single pass, decoupled look-back). Kept count lands in *d_total.
 cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cudaStream_t st);
+// The same compaction out of place as count pass + tile-offset scan + scatter pass (no chained scan); `out` must not alias `in`.
+size_t compact2_scratch_bytes(u64 n);
+cudaError_t launch_compact_two_pass(const CompactArgs& a, void* scratch, u64* d_total, cudaStream_t st);
 // Growth candidates c[0..n) (buffer holds n_pow2 >= n entries, n_pow2 a power of two): entries whose
 // dst is outside [dst_lo,dst_hi) and the padding get order = +inf, the owned ones are counted into
 // *d_owned (zeroed by the caller) and the buffer is sorted by `order` (bitonic).

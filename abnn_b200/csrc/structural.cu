@@ -10,6 +10,8 @@
 //   * k_grow_*       : growth candidates staged by firing events are ordered by the tick ordinal of
 //                      the event that produced them (bitonic sort) and appended in that order.
 #include <algorithm>
+#include <cstdint>
+#include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -149,6 +151,111 @@ cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cu
     return cudaGetLastError();
 }
 
+// ---- out-of-place stable compaction without a chained scan -------------------------------------------------
+// Count pass (16 B read per record) -> exclusive scan of the per-tile counts (cub, ~0.5M values at 1e9 records) -> scatter
+// pass (16 B read + 16 B written per kept record). 48 bytes per record instead of the 32 of k_compact, but every tile is
+// independent: no ticket, no look-back, no barrier wait on a polling warp (which is what holds k_compact at a third of
+// the copy bandwidth, profiles/r1_notes.md §7). Out of place only (a tile may overwrite records that another tile has not
+// read yet), so the in-place prune keeps k_compact. Same tiling and the same in-tile ranks as k_compact.
+__global__ void __launch_bounds__(CT) k_count_kept(const CompactArgs a, u64* tile_cnt)
+{
+    __shared__ u32 s_warp[CT / 32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 wbase = (u64)blockIdx.x * TILE + (u64)warp * (32 * CI);
+    const uint4* in = reinterpret_cast<const uint4*>(a.in);
+    uint4 rec[CI];
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+        const u64 idx = wbase + (u64)j * 32 + lane;
+        if (idx < a.n) rec[j] = __ldcs(in + idx);
+    }
+    u32 kept = 0;
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+        const u64 idx = wbase + (u64)j * 32 + lane;
+        const bool k = idx < a.n && keep_record(a, rec[j]);
+        kept += __popc(__ballot_sync(0xffffffffu, k));
+        if (a.drop_hist) {                                   // removed records per neuron, one atomic per destination and row
+            const bool drop = idx < a.n && !k;
+            const unsigned dm = __ballot_sync(0xffffffffu, drop);
+            if (drop) {
+                const unsigned peers = __match_any_sync(dm, rec[j].y);
+                if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&a.drop_hist[rec[j].y - a.shift_lo + 1], (u32)__popc(peers));
+            }
+        }
+    }
+    if (lane == 0) s_warp[warp] = kept;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+#pragma unroll
+        for (int w = 0; w < CT / 32; ++w) t += s_warp[w];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(CT) k_scatter_kept(const CompactArgs a, const u64* __restrict__ tile_off, u64* total)
+{
+    __shared__ u32 s_warp[CT / 32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 wbase = (u64)blockIdx.x * TILE + (u64)warp * (32 * CI);
+    const uint4* in = reinterpret_cast<const uint4*>(a.in);
+    uint4* out = reinterpret_cast<uint4*>(a.out);
+    uint4 rec[CI];
+    unsigned bal[CI];
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+        const u64 idx = wbase + (u64)j * 32 + lane;
+        if (idx < a.n) rec[j] = __ldcs(in + idx);
+    }
+    u32 warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+        const u64 idx = wbase + (u64)j * 32 + lane;
+        bal[j] = __ballot_sync(0xffffffffu, idx < a.n && keep_record(a, rec[j]));
+        warp_total += __popc(bal[j]);
+    }
+    if (lane == 0) s_warp[warp] = warp_total;
+    __syncthreads();
+    u32 warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < CT / 32; ++w) { const u32 v = s_warp[w]; if (w < (int)warp) warp_off += v; block_total += v; }
+    const u64 base = tile_off[blockIdx.x];
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) *total = base + block_total;
+    u64 pos = base + warp_off;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+        if ((bal[j] >> lane) & 1u) {
+            u64 p = pos + __popc(bal[j] & lt);
+            if (a.shift) p += a.shift[rec[j].y - a.shift_lo];
+            if (p < a.out_cap) __stcs(out + p, rec[j]);
+        }
+        pos += __popc(bal[j]);
+    }
+}
+size_t compact2_scratch_bytes(u64 n)
+{
+    const u64 tiles = (n + TILE - 1) / TILE;
+    size_t scan = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, (u64*)nullptr, (u64*)nullptr, (long long)tiles);
+    return 2 * (size_t)(tiles + 1) * sizeof(u64) + ((scan + 255) & ~(size_t)255) + 256;
+}
+cudaError_t launch_compact_two_pass(const CompactArgs& a, void* scratch, u64* d_total, cudaStream_t st)
+{
+    const u64 tiles = (a.n + TILE - 1) / TILE;
+    if (tiles == 0) return cudaMemsetAsync(d_total, 0, sizeof(u64), st);
+    u64* cnt = reinterpret_cast<u64*>(scratch);
+    u64* off = cnt + tiles + 1;
+    void* tmp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(off + tiles + 1) + 255) & ~(uintptr_t)255);
+    size_t scan = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, cnt, off, (long long)tiles);
+    k_count_kept<<<(unsigned)tiles, CT, 0, st>>>(a, cnt);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, scan, cnt, off, (long long)tiles, st);
+    if (e != cudaSuccess) return e;
+    k_scatter_kept<<<(unsigned)tiles, CT, 0, st>>>(a, off, d_total);
+    return cudaGetLastError();
+}
+
 // ---- ABNN_TABLE_DST_SORTED: stable sort of the table by destination neuron -------------------------
 // LSD radix sort (cub) on key = dst with the 16-byte record as the value: stable, so records that
 // share a destination keep their table order. One-off cost at graph load / after a growth step:
@@ -269,7 +376,8 @@ cudaError_t launch_prune_merge_sorted(const abnn_synapse* syn, u64 n, float w_pr
     CompactArgs a{};
     a.in = syn; a.out = out; a.n = n; a.out_cap = out_cap; a.pred = KEEP_NOT_PRUNED; a.w_prune = w_prune;
     a.shift = cnt; a.shift_lo = dst_lo; a.drop_hist = pruned;
-    e = launch_compact(a, compact_scratch, d_total, st);
+    static const bool lookback = getenv("ABNN_COMPACT_LOOKBACK") != nullptr;     // measurements: the single-pass chained scan
+    e = lookback ? launch_compact(a, compact_scratch, d_total, st) : launch_compact_two_pass(a, compact_scratch, d_total, st);
     if (e != cudaSuccess) return e;
     e = cub::DeviceScan::InclusiveSum(scan_tmp, scan_tmp_bytes, pruned, pruned, (long long)dst_span + 2, st);
     if (e != cudaSuccess) return e;
