@@ -336,7 +336,7 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nul
     }
     if (kept_out) {
         if (!h->mg_pruned) CU(cudaMalloc(&h->mg_pruned, ((size_t)span + 2) * sizeof(u32)));
-        RET(ensure_scratch(h, std::max(compact_scratch_bytes(n), compact2_scratch_bytes(n))));
+        RET(ensure_scratch(h, std::max(compact_scratch_bytes(h->cap), compact2_scratch_bytes(h->cap))));   // by capacity: never regrown
     }
     abnn_synapse* out = h->d_spare;
     h->d_spare = nullptr;
@@ -1322,9 +1322,11 @@ int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out)
         list = h->d_grow_all;
     }
     if (total) {
-        const u32 np2 = next_pow2(total);
+        // sized by the capacity of the list, not by this step's count: growing the scratch means cudaFree + cudaMalloc next
+        // to a 16 GB table, which costs more than the whole structural step (measured: 105 ms instead of 9 ms)
+        RET(ensure_scratch(h, grow_sort_scratch_bytes(std::max<u32>(next_pow2(total), h->p.world_size > 1 ? h->grow_all_buf : h->grow_buf))));
         CU(cudaMemsetAsync(h->d_total + 1, 0, sizeof(u64), h->st));
-        CU(launch_grow_sort_count(list, total, np2, (u32)h->lo, (u32)h->hi, reinterpret_cast<u32*>(h->d_total + 1), h->st));
+        CU(launch_grow_sort_count(list, total, (u32)h->lo, (u32)h->hi, reinterpret_cast<u32*>(h->d_total + 1), h->d_scratch, h->st));
         u64 owned64 = 0;
         CU(cudaMemcpyAsync(&owned64, h->d_total + 1, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
@@ -1369,7 +1371,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
             a.out_cap = h->cap;
             u64 kept = 0;
             cudaError_t e = cudaSuccess;
-            int rc = ensure_scratch(h, spare ? compact2_scratch_bytes(a.n) : compact_scratch_bytes(a.n));
+            int rc = ensure_scratch(h, spare ? compact2_scratch_bytes(h->cap) : compact_scratch_bytes(h->cap));   // by capacity: never regrown
             if (!rc) {
                 e = spare ? launch_compact_two_pass(a, h->d_scratch, h->d_total, h->st) : launch_compact(a, h->d_scratch, h->d_total, h->st);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st);

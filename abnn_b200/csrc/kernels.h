@@ -60,10 +60,10 @@ cudaError_t launch_compact(const CompactArgs& a, void* scratch, u64* d_total, cu
 // The same compaction out of place as count pass + tile-offset scan + scatter pass (no chained scan); `out` must not alias `in`.
 size_t compact2_scratch_bytes(u64 n);
 cudaError_t launch_compact_two_pass(const CompactArgs& a, void* scratch, u64* d_total, cudaStream_t st);
-// Growth candidates c[0..n) (buffer holds n_pow2 >= n entries, n_pow2 a power of two): entries whose
-// dst is outside [dst_lo,dst_hi) and the padding get order = +inf, the owned ones are counted into
-// *d_owned (zeroed by the caller) and the buffer is sorted by `order` (bitonic).
-cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 n_pow2, u32 dst_lo, u32 dst_hi, u32* d_owned, cudaStream_t st);
+// Growth candidates c[0..n): entries whose dst is outside [dst_lo,dst_hi) get order = +inf, the owned ones are counted
+// into *d_owned (zeroed by the caller) and the list is sorted by `order` (radix sort; scratch = grow_sort_scratch_bytes(n)).
+size_t grow_sort_scratch_bytes(u32 n);
+cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 dst_lo, u32 dst_hi, u32* d_owned, void* scratch, cudaStream_t st);
 cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st);
 
 // Stable sort of n records by dst (ABNN_TABLE_DST_SORTED). alt/keys/keys_alt: n-element scratch buffers.
