@@ -100,7 +100,18 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.dev = None
+            try:                            # CUDA_VISIBLE_DEVICES may renumber the devices: find the NVML device by UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                try:
+                    self.dev = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    self.dev = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.dev = None
+            if self.dev is None:
+                self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             # nvmlClocksEventReason* bit values (nvml.h)
             self.bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
