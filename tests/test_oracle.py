@@ -220,3 +220,24 @@ def test_dst_sorted_table_is_a_stable_sort(oracle):
     # existing records keep their relative order; the new ones (w == w_init) sit at the end of their destination's run
     old = after[after["w"] != np.float32(0.1)]
     assert old.tobytes() == before[before["w"] != np.float32(0.1)].tobytes()
+
+
+def test_oracle_b_matches_frozen_northstar_checksums(oracle):
+    """The north-star semantics have no reference implementation to pin against ("parity unpinned"):
+    Oracle B is their definition. tests/golden/northstar_oracle.json freezes that definition — BASELINE configs[0]
+    (reference graph, iid sampler, sine input, 1M-event passes), the throughput configuration (line sampler, dst-sorted
+    table, pruning + growth every pass) and the same on two dst-shards — so a change of oracle_b.cpp, of its compile
+    flags or of the host toolchain that alters any result is caught here, on the CPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_northstar_golden", os.path.join(GOLD, "make_northstar_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = json.load(open(os.path.join(GOLD, "northstar_oracle.json")))
+    assert set(want) == set(gen.CASES)
+    for name, fn in gen.CASES.items():
+        got = json.loads(json.dumps(fn()))
+        assert got == want[name], f"{name}: Oracle B no longer reproduces its frozen checksums"
+    # the cases are not degenerate: events gate, fire, grow and get pruned
+    last = want["toy_line_sorted"][-1]
+    assert last["stats"]["gated"] > 100_000 and last["stats"]["fired"] > 1000 and last["structural"]["pruned"] > 0
+    assert want["toy_reference"][-1]["structural"]["appended"] > 0
