@@ -209,7 +209,10 @@ int read_scalars(abnn_handle* h, DevScalars* out)
 bool slack_mode(const abnn_handle* h, const KParams& kp)
 {
     static const bool off = getenv("ABNN_NO_SLACK") != nullptr;
-    return h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && line_kernel_selected(kp) && kp.ticks < 0xFFFFFFF0ull && !off;
+    // ABNN_IID_SLACK (experiment, not measured yet): the iid / block kernels gate on the 32-bit words too
+    static const bool iid = getenv("ABNN_IID_SLACK") != nullptr;
+    const bool kernel_reads_slack = line_kernel_selected(kp) || (iid && kp.sampler == ABNN_SAMPLER_PHILOX && kp.snapshot);
+    return h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && kernel_reads_slack && kp.ticks < 0xFFFFFFF0ull && !off;
 }
 
 // Bring every rank's lastFired slice into the replicated 64-bit snapshot (collective when world_size > 1).

@@ -274,6 +274,24 @@ __device__ __forceinline__ uint4 load_synapse(const abnn_synapse* p)
     return __ldcs(reinterpret_cast<const uint4*>(p));
 }
 
+// Pre-spike window test of the iid / block kernels (brain.metal:73-77) in two stages, so that the reads of a batch stay
+// in flight together. With kp.use_slack (ABNN_IID_SLACK experiment) the 4-byte gate word of the pass (k_build_slack)
+// replaces the 8-byte snapshot read, as in the line kernel: half the bytes, and the 20 MB gate array sits in the
+// persisting L2 window.
+__device__ __forceinline__ u64 window_word(const KParams& kp, const DevPtrs& d, u32 src)
+{
+    return kp.use_slack ? (u64)__ldcg(d.slack + src) : __ldcg(d.view + src);
+}
+__device__ __forceinline__ bool window_test(const KParams& kp, const DevPtrs& d, bool ok, u32 src, u64 word, u64 now, u64 clock)
+{
+    if (!ok) return false;
+    if (kp.use_slack) {
+        if ((u32)word != SLACK_EXACT) return (u32)(now - clock) < (u32)word;
+        word = __ldcg(d.view + src);                                     // snapshot in the future of the pass start (rare)
+    }
+    return now - word <= kp.window_pre || (!kp.snapshot && word > now);  // live view: a later spike is recent
+}
+
 #ifndef ABNN_TRAV_MIN_CTAS
 #define ABNN_TRAV_MIN_CTAS 3
 #endif
@@ -312,13 +330,13 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
             if (ok[j]) s[j] = load_synapse(d.syn + edge[j]);                     // brain.metal:70
 #pragma unroll
         for (int j = 0; j < U; ++j)
-            if (ok[j]) lp[j] = __ldcg(d.view + s[j].x);                          // brain.metal:73
+            if (ok[j]) lp[j] = window_word(kp, d, s[j].x);                       // brain.metal:73
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const u64 i = base + (u64)j * 256 + threadIdx.x;
             const u64 now = event_now(kp, pc.clock, i);
             if (VISITS) visit(d, ok[j], s[j].y, now);                            // README.md:84
-            const bool cand = ok[j] && (now - lp[j] <= kp.window_pre || (!kp.snapshot && lp[j] > now));   // brain.metal:74 (live view: a later spike is recent)
+            const bool cand = window_test(kp, d, ok[j], s[j].x, lp[j], now, pc.clock);           // brain.metal:74
             const u32 r = resolve_candidates(kp, d, pc, cand, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
             n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
         }
@@ -371,12 +389,12 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
             }
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk)
-                if (ok[kk]) lp[kk] = __ldcg(d.view + s[kk].x);
+                if (ok[kk]) lp[kk] = window_word(kp, d, s[kk].x);
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk) {
                 const u64 now = event_now(kp, pc.clock, ev[kk]);
                 if (VISITS) visit(d, ok[kk], s[kk].y, now);
-                const bool cand = ok[kk] && (now - lp[kk] <= kp.window_pre || (!kp.snapshot && lp[kk] > now));
+                const bool cand = window_test(kp, d, ok[kk], s[kk].x, lp[kk], now, pc.clock);
                 const u32 r = resolve_candidates(kp, d, pc, cand, ev[kk], ed[kk], s[kk].x, s[kk].y, __uint_as_float(s[kk].z), now);
                 n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
             }
