@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("ABNN_B200_OUT") or os.path.join(HERE, "libabnn_b200.so")   # override: tuning variants only
 OBJ = os.path.join(HERE, "_obj" + os.environ.get("ABNN_B200_OBJ_SUFFIX", ""))
-SOURCES = ["traversal.cu", "exact.cu", "io_kernels.cu", "structural.cu", "init.cu", "capi.cu"]
+SOURCES = ["traversal.cu", "exact.cu", "io_kernels.cu", "structural.cu", "init.cu", "exchange.cu", "capi.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false",
               "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]

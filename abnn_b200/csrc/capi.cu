@@ -92,6 +92,11 @@ struct abnn_handle {
     u64* d_total = nullptr;               // [0]: compaction total, [1..]: misc
     u64* d_counts = nullptr;              // world_size u64 (record counts exchange)
     ncclComm_t comm = nullptr;
+    // peer-memory exchange (opt-in, p2p_setup): flag block, IPC mappings of the peers' timestamp allocations and flag blocks
+    bool p2p = false;
+    u64* d_p2p = nullptr;
+    void* peer_ts[P2P_MAX_WORLD]{}; void* peer_flags[P2P_MAX_WORLD]{};
+    P2PTable p2p_tab{};
     // EXACT execution scratch (allocated on first use)
     u64* d_xkeys = nullptr; u64* d_xvals = nullptr; u32* d_xcount = nullptr; void* d_xtmp = nullptr;
     u64 x_cap = 0; size_t x_tmp_bytes = 0;
@@ -215,6 +220,74 @@ bool slack_mode(const abnn_handle* h, const KParams& kp)
     return h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && kernel_reads_slack && kp.ticks < 0xFFFFFFF0ull && !off;
 }
 
+// Peer-memory exchange (exchange.cu): every rank maps the peers' timestamp allocation and flag block through CUDA IPC.
+// The 2 x 64-byte handles travel through one ncclAllGather; a rank that cannot map a peer makes EVERY rank fall back to
+// the NCCL exchange (ncclAllReduce(min) of the outcome), so the ranks never disagree on which exchange runs.
+int p2p_setup(abnn_handle* h)
+{
+    const u32 W = h->p.world_size, me = h->p.rank;
+    if (W < 2 || W > P2P_MAX_WORLD || !h->d.slack) return 0;
+    CU(cudaMalloc(&h->d_p2p, P2P_WORDS * sizeof(u64)));
+    CU(cudaMemsetAsync(h->d_p2p, 0, P2P_WORDS * sizeof(u64), h->st));
+    struct Pair { cudaIpcMemHandle_t ts, flags; };
+    static_assert(sizeof(Pair) == 128, "two 64-byte IPC handles");
+    Pair mine{};
+    CU(cudaIpcGetMemHandle(&mine.ts, h->d_ts));
+    CU(cudaIpcGetMemHandle(&mine.flags, h->d_p2p));
+    Pair* d_all = nullptr;
+    CU(cudaMalloc(&d_all, (size_t)W * sizeof(Pair)));
+    CU(cudaMemcpyAsync(d_all + me, &mine, sizeof(Pair), cudaMemcpyHostToDevice, h->st));
+    NC(ncclAllGather(d_all + me, d_all, sizeof(Pair), ncclUint8, h->comm, h->st));
+    std::vector<Pair> all(W);
+    CU(cudaMemcpyAsync(all.data(), d_all, (size_t)W * sizeof(Pair), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    int ok = 1;
+    for (u32 r = 0; r < W && ok; ++r) {
+        if (r == me) { h->peer_ts[r] = h->d_ts; h->peer_flags[r] = h->d_p2p; continue; }
+        if (cudaIpcOpenMemHandle(&h->peer_ts[r], all[r].ts, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&h->peer_flags[r], all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        }
+    }
+    int* d_ok = reinterpret_cast<int*>(d_all);
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->st));
+    NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->st));
+    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaFree(d_all));
+    if (!ok) {                                               // NCCL exchange on every rank
+        for (u32 r = 0; r < W; ++r) {
+            if (r != me && h->peer_ts[r]) cudaIpcCloseMemHandle(h->peer_ts[r]);
+            if (r != me && h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+            h->peer_ts[r] = h->peer_flags[r] = nullptr;
+        }
+        cudaGetLastError();
+        return 0;
+    }
+    const size_t off_view = reinterpret_cast<char*>(h->d.view) - reinterpret_cast<char*>(h->d_ts);   // same layout on every rank
+    h->p2p_tab = P2PTable{};
+    h->p2p_tab.world = W; h->p2p_tab.rank = me;
+    for (u32 r = 0; r < W; ++r) {
+        h->p2p_tab.slack[r] = reinterpret_cast<u32*>(h->peer_ts[r]);
+        h->p2p_tab.view[r] = reinterpret_cast<u64*>(reinterpret_cast<char*>(h->peer_ts[r]) + off_view);
+        h->p2p_tab.flags[r] = reinterpret_cast<u64*>(h->peer_flags[r]);
+    }
+    h->p2p = true;
+    return 0;
+}
+
+// A bounded spin of the peer-memory exchange expired (a peer never arrived): reported at the next synchronising call.
+int p2p_check(abnn_handle* h)
+{
+    if (!h->p2p) return 0;
+    u64 err = 0;
+    CU(cudaMemcpyAsync(&err, h->d_p2p + P2P_ERROR, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (err) return fail(ABNN_ERR_COMM, "peer-memory exchange timed out waiting for a peer rank");
+    return 0;
+}
+
 // Bring every rank's lastFired slice into the replicated 64-bit snapshot (collective when world_size > 1).
 int ensure_view(abnn_handle* h)
 {
@@ -239,7 +312,12 @@ int exchange_timestamps(abnn_handle* h, const KParams& kp)
     h->slack_ready = false;
     if (h->p.world_size > 1) {
         if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
-        if (slack_mode(h, kp) && h->slice >= head && !full) {
+        if (slack_mode(h, kp) && h->slice >= head && !full && h->p2p) {
+            // peer-memory stores over NVLink instead of the collective (exchange.cu)
+            CU(launch_p2p_exchange(kp, h->d, h->p2p_tab, h->lo, h->hi, head, h->sm_count, h->st));
+            h->slack_ready = true;
+            h->view_stale = true;
+        } else if (slack_mode(h, kp) && h->slice >= head && !full) {
             CU(launch_build_slack(kp, h->d, h->d.live, h->lo, h->hi, h->st));
             NC(ncclGroupStart());
             NC(ncclAllGather(h->d.slack + h->lo, h->d.slack, h->slice, ncclUint32, h->comm, h->st));
@@ -639,6 +717,11 @@ void abnn_destroy(abnn_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
+    for (u32 r = 0; r < P2P_MAX_WORLD; ++r) {
+        if (h->p2p && r != h->p.rank && h->peer_ts[r]) cudaIpcCloseMemHandle(h->peer_ts[r]);
+        if (h->p2p && r != h->p.rank && h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+    }
+    cudaFree(h->d_p2p);
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_syn); cudaFree(h->d_spare); cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp); cudaFree(h->mg_cnt);
     cudaFree(h->mg_pruned); cudaFree(h->mg_scan); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
@@ -695,6 +778,7 @@ int abnn_comm_init(abnn_handle* h, const void* id128)
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     NC(ncclCommInitRank(&h->comm, (int)h->p.world_size, id, (int)h->p.rank));
+    if (getenv("ABNN_P2P_EXCHANGE")) RET(p2p_setup(h));     // experiment, not measured yet: peer-memory exchange instead of NCCL
     return 0;
 }
 
@@ -1219,6 +1303,7 @@ int abnn_sync(abnn_handle* h)
 {
     RET(use(h));
     CU(cudaStreamSynchronize(h->st));
+    RET(p2p_check(h));
     return 0;
 }
 

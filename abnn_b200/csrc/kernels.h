@@ -12,6 +12,20 @@ cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* s
 bool line_kernel_selected(const KParams& kp);
 cudaError_t launch_end_pass(const KParams& kp, DevScalars* sc, abnn_pass_stats* out, cudaStream_t st);
 
+// exchange.cu — the per-pass exchange of a sharded PARALLEL run as peer-memory stores (opt-in, see capi.cu:p2p_setup)
+constexpr u32 P2P_MAX_WORLD = 8;
+enum : u32 { P2P_DONE = 0, P2P_PUSHED = P2P_MAX_WORLD, P2P_EPOCH = 2 * P2P_MAX_WORLD, P2P_CTAS, P2P_ERROR, P2P_WORDS = 32 };   // u64 words of a rank's flag block
+struct P2PTable {
+    u32* slack[P2P_MAX_WORLD];      // every rank's gate-word array (own pointer at [rank], IPC-mapped peers elsewhere)
+    u64* view[P2P_MAX_WORLD];       // every rank's 64-bit snapshot (the input/output head is delivered there)
+    u64* flags[P2P_MAX_WORLD];      // every rank's flag block (P2P_WORDS u64)
+    u32 world, rank;
+};
+// gate words of neurons [n0, n1) (the owned slice) into every rank's array, rank 0's lastFired[0, head) into every snapshot,
+// fenced by two flag rounds; returns when everything is enqueued on st
+cudaError_t launch_p2p_exchange(const KParams& kp, const DevPtrs& d, const P2PTable& t, u64 n0, u64 n1, u64 head, int sm_count,
+                                cudaStream_t st);
+
 // exact.cu — EXACT execution (two-phase, bit-identical to SERIAL)
 size_t exact_sort_temp_bytes(u64 cap);
 cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, u64* vals, u32* counter, int sm_count, cudaStream_t st);
