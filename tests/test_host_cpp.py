@@ -17,6 +17,18 @@ def test_host_cpp_facade_compiles():
     assert os.path.exists(exe)
 
 
+def test_p2p_protocol_model(tmp_path):
+    """Host model (threads, random delays) of the flag protocol of the opt-in peer-memory exchange (csrc/exchange.cu):
+    a rank never reads a gate word of another pass while it traverses, never starts a pass with a stale word, nobody
+    deadlocks. Logic only — the CUDA memory-ordering side needs GPUs."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "p2p_protocol_sim"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", os.path.join(root, "tests", "host_cpp", "p2p_protocol_sim.cpp"),
+                    "-o", str(exe)], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_host_cpp_engine_matches_oracle(tmp_path):
     exe = build_host_tests()
