@@ -1256,8 +1256,13 @@ int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, flo
     static const bool no_graph = getenv("ABNN_NO_GRAPH") != nullptr;
     // Single-GPU handles only: with the NCCL exchange inside the captured sequence a 2-rank run hung in
     // this environment (NCCL 2.28.9, driver 580); sharded handles enqueue the same sequence eagerly.
-    const bool capturable = h->p.exec_mode == ABNN_EXEC_PARALLEL && h->p.world_size == 1 && !no_graph;
+    // With the peer-memory exchange (p2p_setup) the sharded sequence holds no NCCL call once the gate words are being
+    // exchanged (slack_ready), so it can be captured too: opt-in on top of ABNN_P2P_EXCHANGE, not measured yet.
+    static const bool p2p_graph = getenv("ABNN_P2P_GRAPH") != nullptr;
     const bool pre[2] = {h->slack_ready, h->view_stale};
+    const bool sharded_ok = p2p_graph && h->p2p && pre[0] && slack_mode(h, kp) && h->slice >= (u64)h->p.n_input + h->p.n_output &&
+                            !getenv("ABNN_FULL_EXCHANGE");
+    const bool capturable = h->p.exec_mode == ABNN_EXEC_PARALLEL && (h->p.world_size == 1 || sharded_ok) && !no_graph;
     const bool match = h->step_exec && h->step_events == events && h->step_counts == h->n_local_all &&
                        h->step_pre[0] == pre[0] && h->step_pre[1] == pre[1];
     ++h->step_calls;
