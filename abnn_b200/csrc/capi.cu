@@ -460,10 +460,7 @@ int run_exact(abnn_handle* h, const KParams& kp)
 {
     if (kp.count >= (1ull << 32)) return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution: at most 2^32-1 events per rank per pass");
     if (kp.count > h->x_cap) {
-        if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
-    cudaFree(h->d_frame); cudaFreeHost(h->h_frame);
-    for (int i = 0; i < RING; ++i) if (h->frame_ev[i]) cudaEventDestroy(h->frame_ev[i]);
-    cudaFree(h->d_xkeys); cudaFree(h->d_xvals); cudaFree(h->d_xtmp);
+        cudaFree(h->d_xkeys); cudaFree(h->d_xvals); cudaFree(h->d_xtmp);
         h->d_xkeys = h->d_xvals = nullptr; h->d_xtmp = nullptr; h->x_cap = 0;
         const u64 cap = kp.count;
         CU(cudaMalloc(&h->d_xkeys, 2 * cap * sizeof(u64)));
