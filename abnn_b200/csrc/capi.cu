@@ -390,8 +390,8 @@ int sort_table(abnn_handle* h)
 }
 
 // ABNN_TABLE_DST_SORTED growth: the m candidates list[0..m) (in append order) become records, are sorted by dst
-// (stable) and merged into the sorted table out of place; the tables are then swapped. Scratch lives only here.
-// Sorted insertion of the first m growth candidates of `list` into the dst-sorted table. With kept_out != null the
+// (stable) and merged into the sorted table out of place; the tables are then swapped (scratch and the spare table
+// are cached in the handle). With kept_out != null the
 // pruning (w < w_prune) happens in the same pass over the table (launch_prune_merge_sorted) and *kept_out receives the
 // number of existing records that survived.
 int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nullptr)
