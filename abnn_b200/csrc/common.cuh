@@ -50,6 +50,18 @@ __host__ __device__ __forceinline__ float rand01_xorshift(u32 s)
     return (float)(s & 0xFFFFFFu) * (1.0f / 16777216.0f);
 }
 
+// Release-draw and synaptogenesis-trial words of the events of one sample group (include/abnn.h, sample_block): the
+// group's ONE Philox call q serves all of its events — event `lane` of the group takes fmix32(q.z + lane*0x9E3779B9) /
+// fmix32(q.w + lane*0x85EBCA6B) (MurmurHash3's 32-bit finaliser, a bijection). Groups of one event (iid sampler, SWEEP)
+// use q.z / q.w as they are. Same definition as oracle/oracle_b.cpp:release_word / trial_word.
+__host__ __device__ __forceinline__ u32 fmix32(u32 h)
+{
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ u32 release_word(u32 qz, u32 group, u32 lane) { return group == 1 ? qz : fmix32(qz + lane * 0x9E3779B9u); }
+__host__ __device__ __forceinline__ u32 trial_word(u32 qw, u32 group, u32 lane) { return group == 1 ? qw : fmix32(qw + lane * 0x85EBCA6Bu); }
+
 // 32-bit pre-spike gate word of a neuron for the pass that starts at `clock` (traversal.cu:k_build_slack):
 // an event with tick offset t = now - clock passes the window gate (brain.metal:73-77) iff t < word.
 // 0 = never in this pass, 0xFFFFFFFE = always, 0xFFFFFFFF = snapshot in the future: take the exact 64-bit test.

@@ -92,10 +92,14 @@ __global__ void __launch_bounds__(256) k_exact_phase3(const __grid_constant__ KP
             const u64 edge = vals[t];
             const float w = d.syn[edge].w;
             const u64 eid = event_base + i;
+            const u32 group = kp.sampler == ABNN_SAMPLER_PHILOX ? kp.sample_block : 1u;      // events per Philox call
+            const u32 glane = (u32)i & (group - 1u);
             Philox4 r{0, 0, 0, 0};
-            if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f)
-                r = philox4x32_10((u32)eid, (u32)(eid >> 32), kp.rank, STREAM_EVENT, kp.seed_lo, kp.seed_hi);
-            const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
+            if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) {
+                const u64 eid0 = eid - glane;
+                r = philox4x32_10((u32)eid0, (u32)(eid0 >> 32), kp.rank, STREAM_EVENT, kp.seed_lo, kp.seed_hi);
+            }
+            const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(release_word(r.z, group, glane));
             const float p = clampf(w * w * kp.base_scale, 0.f, 1.f);       // brain.metal:91
             const bool fired = p > u;                                      // brain.metal:92
             float dW = fired ? (kp.a_ltp * (1.f - w)) : (-kp.a_ltd * w);   // brain.metal:101-102
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) k_exact_phase3(const __grid_constant__ KP
             if (fired) {
                 if (ld < now) ld = now;                                    // brain.metal:125-126
                 ++fired_n;
-                if (kp.p_new > 0.f && (float)r.w * (1.0f / 4294967296.0f) < kp.p_new) {   // README.md:125
+                if (kp.p_new > 0.f && (float)trial_word(r.w, group, glane) * (1.0f / 4294967296.0f) < kp.p_new) {   // README.md:125
                     const Philox4 g = philox4x32_10((u32)eid, (u32)(eid >> 32), kp.rank, STREAM_GROW, kp.seed_lo, kp.seed_hi);
                     const u32 nd = (u32)(kp.n_input + mulhi64(((u64)g.x << 32) | g.y, kp.n_neuron - kp.n_input));
                     const u32 slot = atomicAdd(&d.sc->grow_count, 1u);

@@ -51,6 +51,16 @@ __device__ __forceinline__ Philox4 event_philox(const KParams& kp, u64 eid)
 {
     return philox4x32_10((u32)eid, (u32)(eid >> 32), kp.rank, STREAM_EVENT, kp.seed_lo, kp.seed_hi);
 }
+// The two per-event random words (release draw, synaptogenesis trial) of local event i: taken from the Philox call of
+// the event's sample group (common.cuh:release_word).
+struct EventWords { u32 rel, trial; };
+__device__ __forceinline__ EventWords event_words(const KParams& kp, u64 event_base, u64 i)
+{
+    const u32 group = kp.sampler == ABNN_SAMPLER_PHILOX ? kp.sample_block : 1u;
+    const u32 lane = (u32)i & (group - 1u);
+    const Philox4 q = event_philox(kp, event_base + i - lane);
+    return EventWords{release_word(q.z, group, lane), trial_word(q.w, group, lane)};
+}
 __device__ __forceinline__ void stage_growth(const KParams& kp, const DevPtrs& d, u64 eid, u64 order, u32 src, u32 trial)
 {
     // README.md:125 "rand() < p_new on fire -> append (src, dst') with w_init"
@@ -75,17 +85,17 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
     u32 fires = 0;
     u64 gated = 0, fired_n = 0, cands = 0;
     const bool need_philox = kp.sampler == ABNN_SAMPLER_PHILOX || kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f;
+    const u32 group = kp.sampler == ABNN_SAMPLER_PHILOX ? kp.sample_block : 1u;      // events per Philox call
     for (u64 i = 0; i < kp.count; ++i) {
         const u64 eid = event_base + i;
-        Philox4 r{0, 0, 0, 0};
-        if (need_philox) r = event_philox(kp, eid);
+        const u32 lane = (u32)i & (group - 1u);
+        Philox4 q{0, 0, 0, 0};
+        if (need_philox) q = event_philox(kp, eid - lane);
         u64 edge;
         if (kp.sampler == ABNN_SAMPLER_SWEEP) { edge = i; if (edge >= kp.n_local) continue; }
-        else if (kp.sample_block == 1) { if (!kp.n_local) break; edge = mulhi64(((u64)r.x << 32) | r.y, kp.n_local); }
+        else if (kp.sample_block == 1) { if (!kp.n_local) break; edge = mulhi64(((u64)q.x << 32) | q.y, kp.n_local); }
         else {
             if (!kp.n_local) break;
-            const u64 lane = i & (kp.sample_block - 1);
-            const Philox4 q = event_philox(kp, eid - lane);
             edge = (mulhi64(((u64)q.x << 32) | q.y, kp.n_blocks) << kp.log_block) + lane;
             if (edge >= kp.n_local) continue;
         }
@@ -98,7 +108,7 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
         const u64 ld = d.live[s.dst];
         if (now - ld <= kp.refractory) continue;
         if (kp.budget_on && fires >= kp.budget_share) continue;
-        const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
+        const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(release_word(q.z, group, lane));
         const bool fired = release_test(kp, s.w, u);
         if (fired) ++fires;
         const float w = plasticity(kp, s.w, fired, R, rbar, now - ld);
@@ -109,7 +119,7 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
         if (fired) {
             if (d.live[s.dst] < now) d.live[s.dst] = now;                     // brain.metal:125-126
             ++fired_n;
-            stage_growth(kp, d, eid, tick_base + i * kp.world + kp.rank, s.src, r.w);
+            stage_growth(kp, d, eid, tick_base + i * kp.world + kp.rank, s.src, trial_word(q.w, group, lane));
         }
     }
     sc->rbar = rbar;
@@ -143,9 +153,9 @@ __device__ __forceinline__ u32 candidate_turn(const KParams& kp, const DevPtrs& 
     if (kp.budget_on && *(volatile u32*)&d.sc->fires_claimed >= kp.budget_share) return 0;  // brain.metal:85-88
     if (reload_w) w = __ldcg(&d.syn[edge].w);        // an earlier same-destination peer may have updated this record
     const u64 eid = pc.event_base + i;
-    Philox4 r{0, 0, 0, 0};
-    if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_philox(kp, eid);
-    const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
+    EventWords r{0, 0};
+    if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_words(kp, pc.event_base, i);
+    const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.rel);
     bool fired = release_test(kp, w, u);
     if (fired && kp.budget_on) {                                                            // brain.metal:95-98, saturating
         const u32 old = atomicAdd(&d.sc->fires_claimed, 1u);
@@ -154,7 +164,7 @@ __device__ __forceinline__ u32 candidate_turn(const KParams& kp, const DevPtrs& 
     __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, gap));                   // brain.metal:122
     if (!fired) return 1;
     atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
-    stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.w);
+    stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.trial);
     return 3;
 }
 
@@ -194,9 +204,9 @@ __device__ __forceinline__ u32 chain_resolve(const KParams& kp, const DevPtrs& d
     const unsigned lane  = threadIdx.x & 31;
     const unsigned peers = __match_any_sync(cmask, dst);
     const u64 eid = pc.event_base + i;
-    Philox4 r{0, 0, 0, 0};
-    if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_philox(kp, eid);
-    const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.z);
+    EventWords r{0, 0};
+    if (kp.release_rng == ABNN_RNG_PHILOX || kp.p_new > 0.f) r = event_words(kp, pc.event_base, i);
+    const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((u32)i ^ (u32)now) : u01_24(r.rel);
     const bool rel = release_test(kp, w, u);                                                // brain.metal:91-92
     bool settled = false, skip = true, fired = false;
     u64 gap = 0;
@@ -218,7 +228,7 @@ __device__ __forceinline__ u32 chain_resolve(const KParams& kp, const DevPtrs& d
     __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, gap));                   // brain.metal:122
     if (!fired) return 1;
     atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
-    stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.w);
+    stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.trial);
     return 3;
 }
 __device__ __forceinline__ u32 chain_path(const KParams& kp, const DevPtrs& d, const PassConsts& pc, bool cand, u64 i,

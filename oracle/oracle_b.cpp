@@ -63,6 +63,14 @@ inline float rand01_xorshift(uint32_t s)
 
 struct GrowCand { uint64_t order; uint32_t src, dst; };   // order = tick ordinal of the firing event
 
+// Release-draw and synaptogenesis-trial words of the events of one sample group (include/abnn.h, sample_block):
+// the group's ONE Philox call q serves all of its events — event `lane` of the group takes
+// fmix32(q.z + lane*0x9E3779B9) / fmix32(q.w + lane*0x85EBCA6B) (fmix32 = the MurmurHash3 32-bit finaliser, a
+// bijection of the 32-bit word). Groups of one event (iid sampler, SWEEP) use q.z / q.w as they are.
+inline uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
+inline uint32_t release_word(const uint32_t q[4], uint64_t B, uint32_t lane) { return B == 1 ? q[2] : fmix32(q[2] + lane * 0x9E3779B9u); }
+inline uint32_t trial_word(const uint32_t q[4], uint64_t B, uint32_t lane) { return B == 1 ? q[3] : fmix32(q[3] + lane * 0x85EBCA6Bu); }
+
 }  // namespace
 
 struct ob_handle {
@@ -327,21 +335,22 @@ int ob_run_pass(ob_handle* h, uint64_t events, abnn_pass_stats* st)
     const float R = h->reward;                                   // brain.metal:105
 
     for (uint64_t i = 0; i < count; ++i) {
-        // K1: event -> synapse
-        uint32_t r[4] = {0, 0, 0, 0};
+        // K1: event -> synapse. One Philox call per sample group (B events): .x.y -> position, .z/.w -> the release
+        // and growth words of the group's events (release_word / trial_word above).
         const uint64_t eid = h->event_base + i;
+        const uint64_t Bw = p.sampler == ABNN_SAMPLER_PHILOX ? B : 1;        // events per Philox call
+        const uint32_t lane = uint32_t(i % Bw);
+        const uint64_t eid0 = eid - lane;
+        uint32_t q[4] = {0, 0, 0, 0};
         const bool need_philox = p.sampler == ABNN_SAMPLER_PHILOX || p.release_rng == ABNN_RNG_PHILOX || p.p_new > 0.f;
         if (need_philox)
-            philox4x32_10(uint32_t(eid), uint32_t(eid >> 32), k, STREAM_EVENT, uint32_t(p.seed), uint32_t(p.seed >> 32), r);
+            philox4x32_10(uint32_t(eid0), uint32_t(eid0 >> 32), k, STREAM_EVENT, uint32_t(p.seed), uint32_t(p.seed >> 32), q);
         uint64_t edge;
         if (p.sampler == ABNN_SAMPLER_SWEEP) { edge = i; if (edge >= n_local) continue; }   // brain.metal:60-61
-        else if (B == 1) { if (!n_local) break; edge = mulhi64((uint64_t(r[0]) << 32) | r[1], n_local); }
+        else if (B == 1) { if (!n_local) break; edge = mulhi64((uint64_t(q[0]) << 32) | q[1], n_local); }   // README.md:77
         else {
             // block sampler (include/abnn.h sample_block): the group's first event draws the block
             if (!n_local) break;
-            const uint64_t lane = i % B, eid0 = eid - lane;
-            uint32_t q[4];
-            philox4x32_10(uint32_t(eid0), uint32_t(eid0 >> 32), k, STREAM_EVENT, uint32_t(p.seed), uint32_t(p.seed >> 32), q);
             edge = B * mulhi64((uint64_t(q[0]) << 32) | q[1], (n_local + B - 1) / B) + lane;
             if (edge >= n_local) continue;
         }
@@ -358,7 +367,7 @@ int ob_run_pass(ob_handle* h, uint64_t events, abnn_pass_stats* st)
         if (budget_on && fires_left == 0) continue;              // brain.metal:85-88
         // K5: release
         const float pr = clampf(s.w * s.w * p.base_scale, 0.f, 1.f);
-        const float u = p.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift(uint32_t(i) ^ uint32_t(now)) : u01_24(r[2]);
+        const float u = p.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift(uint32_t(i) ^ uint32_t(now)) : u01_24(release_word(q, Bw, lane));
         bool fired = pr > u;                                     // brain.metal:91-92
         if (fired && budget_on) --fires_left;                    // brain.metal:95-98 (serial: never loses the race)
         // K6: plasticity
@@ -377,7 +386,7 @@ int ob_run_pass(ob_handle* h, uint64_t events, abnn_pass_stats* st)
             if (h->live[s.dst] < now) h->live[s.dst] = now;                 // brain.metal:125-126 (max: README.md:106 order-free)
             ++fired_n;
             // README.md:125 synaptogenesis: "rand() < p_new on fire -> append (src, dst')"
-            if (p.p_new > 0.f && float(r[3]) * (1.0f / 4294967296.0f) < p.p_new) {
+            if (p.p_new > 0.f && float(trial_word(q, Bw, lane)) * (1.0f / 4294967296.0f) < p.p_new) {
                 uint32_t g[4];
                 philox4x32_10(uint32_t(eid), uint32_t(eid >> 32), k, STREAM_GROW, uint32_t(p.seed), uint32_t(p.seed >> 32), g);
                 const uint64_t dsts = h->N - p.n_input;

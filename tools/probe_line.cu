@@ -22,7 +22,7 @@ __device__ __forceinline__ void cp_async16(u32 dst, const void* src) { asm volat
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-struct Arrays { uint4* tab; u64 n_lines; u32* gate; u64* visited; u64* live; u64 n_neuron; u32 g_thresh; };
+struct Arrays { uint4* tab; u64 n_lines; u32* gate; u64* visited; u64* live; u64 n_neuron; u32 g_thresh; uint2* dstw; u32* fire32; u32* vis32; };
 
 // L0: lane l reads 16 bytes of line (chunk * 32 + iteration * 4 + l / 8): 4 whole lines per warp instruction, U instructions in flight
 template <int U> __global__ void __launch_bounds__(256) k_line_regs(Arrays a, u64 n_chunks, unsigned* sink)
@@ -70,8 +70,22 @@ template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arr
             const uint4 r = *reinterpret_cast<const uint4*>(stage + lane * 16 + k * 512);
             const u64 line = __shfl_sync(0xffffffffu, my_line, k * 4 + sub);
             if (LEVEL >= 3) acc += __ldcg(a.gate + r.x);                                      // one random 4-byte read per record
-            if (LEVEL >= 4 && rec == 7) {                                                     // once per line
-                const u32 dst = (u32)(mix(line) % a.n_neuron);
+            if (LEVEL == 5 && rec == 7) {                                                     // packed {vis32, fire32}: one sector per line
+                const u32 dst = (u32)__umul64hi(mix(line), a.n_neuron);
+                acc += __ldcg(reinterpret_cast<const u32*>(a.dstw + dst) + 1);
+                atomicMax(reinterpret_cast<u32*>(a.dstw + dst), (u32)(c * 256 + k * 32 + lane));
+            }
+            if (LEVEL == 6 && rec == 7) {                                                     // two 20 MB arrays (fire32, vis32)
+                const u32 dst = (u32)__umul64hi(mix(line), a.n_neuron);
+                acc += __ldcg(a.fire32 + dst);
+                atomicMax(a.vis32 + dst, (u32)(c * 256 + k * 32 + lane));
+            }
+            if (LEVEL == 7 && rec == 7) {                                                     // packed, read only (no RED)
+                const u32 dst = (u32)__umul64hi(mix(line), a.n_neuron);
+                acc += __ldcg(reinterpret_cast<const u32*>(a.dstw + dst) + 1);
+            }
+            if (LEVEL == 4 && rec == 7) {                                                     // once per line
+                const u32 dst = (u32)__umul64hi(mix(line), a.n_neuron);
                 acc += (unsigned)__ldcg(a.live + dst);
                 atomicMax(a.visited + dst, c * 256 + k * 32 + lane);
             }
@@ -116,12 +130,19 @@ int main(int argc, char** argv)
     const u64 npad = (neurons + 31) & ~31ull;
     unsigned char* hot; CK(cudaMalloc(&hot, npad * 20)); CK(cudaMemset(hot, 0, npad * 20));
     a.gate = reinterpret_cast<u32*>(hot); a.visited = reinterpret_cast<u64*>(hot + npad * 4); a.live = a.visited + npad;
+    // second layout: [gate 4 B | dstw {vis32, fire32} 8 B] per neuron = 60 MB, and [gate | fire32 | vis32]
+    unsigned char* hot2; CK(cudaMalloc(&hot2, npad * 12)); CK(cudaMemset(hot2, 0, npad * 12));
+    u32* gate2 = reinterpret_cast<u32*>(hot2);
+    a.dstw = reinterpret_cast<uint2*>(hot2 + npad * 4); a.fire32 = reinterpret_cast<u32*>(hot2 + npad * 4); a.vis32 = a.fire32 + npad;
     unsigned* sink; CK(cudaMalloc(&sink, 4));
     cudaStream_t st; CK(cudaStreamCreate(&st));
     CK(cudaFuncSetAttribute(k_line_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
+    CK(cudaFuncSetAttribute(k_line_staged<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
+    CK(cudaFuncSetAttribute(k_line_staged<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
+    CK(cudaFuncSetAttribute(k_line_staged<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     auto report = [&](const char* name, float ms, double bytes_per_event) {
         printf("%-64s %.3f ms  %6.1f Gev/s  %5.2f TB/s algorithmic\n", name, ms, events / ms / 1e6, events * bytes_per_event / ms / 1e9);
     };
@@ -150,6 +171,35 @@ int main(int argc, char** argv)
         report("L2 + 4-byte write-back on a fraction g of the lines", timeit([&] { k_line_staged<2><<<sm * 4, 256, sh, st>>>(a, n_chunks, sink); }), 16 + 16 * g);
         report("L3 + one random 4-byte gate read per record (20 MB array)", timeit([&] { k_line_staged<3><<<sm * 4, 256, sh, st>>>(a, n_chunks, sink); }), 16 + 16 * g);
         report("L4 + RED.MAX.64 and 8-byte read per line (two 40 MB arrays)", timeit([&] { k_line_staged<4><<<sm * 4, 256, sh, st>>>(a, n_chunks, sink); }), 16 + 16 * g);
+    }
+    // ---- packed 32-bit destination words: [gate | {vis32, fire32}] = 60 MB
+    Arrays b = a; b.gate = gate2;
+    for (int window = 0; window < 3; ++window) {
+        cudaStreamAttrValue attr{};
+        if (window) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, 0);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, 0);
+            size_t hotb = npad * 12, want = hotb < (size_t)max_persist ? hotb : (size_t)max_persist;
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            attr.accessPolicyWindow.base_ptr = hot2;
+            attr.accessPolicyWindow.num_bytes = hotb < (size_t)max_window ? hotb : (size_t)max_window;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = window == 1 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+            printf("-- packed layout, persisting window over gate + dstw (60 MB), missProp %s\n", window == 1 ? "streaming" : "normal");
+        } else {
+            CK(cudaCtxResetPersistingL2Cache());
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+            attr.accessPolicyWindow.num_bytes = 0;
+            printf("-- packed layout, no persisting window\n");
+        }
+        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        const size_t sh = 8 * 4608;
+        report("L3 gate read per record (20 MB array)", timeit([&] { k_line_staged<3><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+        report("L7 + 4-byte read per line of packed dstw (40 MB)", timeit([&] { k_line_staged<7><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+        report("L5 + RED.MAX.32 on the same 8-byte word", timeit([&] { k_line_staged<5><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+        report("L6 fire32 / vis32 as two 20 MB arrays (read + RED.MAX.32)", timeit([&] { k_line_staged<6><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
     }
     return 0;
 }
