@@ -66,7 +66,7 @@ struct abnn_handle {
     std::vector<u64> n_local_all;
     bool counts_dirty = false;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj = nullptr, evk = nullptr;
     cudaEvent_t timer[8]{};
     abnn_synapse* d_syn = nullptr;
     abnn_synapse* d_spare = nullptr;      // second table (cap records) kept between sorted growth steps when memory allows
@@ -213,11 +213,16 @@ int read_scalars(abnn_handle* h, DevScalars* out)
 // The line kernel gates on the 32-bit slack words (traversal.cu:k_build_slack) when it can.
 bool slack_mode(const abnn_handle* h, const KParams& kp)
 {
-    static const bool off = getenv("ABNN_NO_SLACK") != nullptr;
-    // ABNN_IID_SLACK (experiment, not measured yet): the iid / block kernels gate on the 32-bit words too
-    static const bool iid = getenv("ABNN_IID_SLACK") != nullptr;
-    const bool kernel_reads_slack = line_kernel_selected(kp) || (iid && kp.sampler == ABNN_SAMPLER_PHILOX && kp.snapshot);
+    static const bool off = tune_env("ABNN_NO_SLACK") != nullptr;
+    // the iid and block kernels gate on the 32-bit words too (measured: 16.2 -> 19.2 e9 events/s at the 1B shape, profiles/r2_notes.md)
+    const bool kernel_reads_slack = kp.sampler == ABNN_SAMPLER_PHILOX && kp.snapshot;
     return h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && kernel_reads_slack && kp.ticks < 0xFFFFFFF0ull && !off;
+}
+// k_traverse_line32 runs this pass: gate words in use and the kernel's own preconditions (traversal.cu:line32_selected)
+bool line32_mode(const abnn_handle* h, const KParams& kp)
+{
+    static const bool off = tune_env("ABNN_NO_LINE32") != nullptr;
+    return slack_mode(h, kp) && h->d.fire32 && line32_selected(kp) && !off;
 }
 
 // Peer-memory exchange (exchange.cu): every rank maps the peers' timestamp allocation and flag block through CUDA IPC.
@@ -307,7 +312,7 @@ int ensure_view(abnn_handle* h)
 // slices is refreshed lazily (ensure_view) when something asks for it.
 int exchange_timestamps(abnn_handle* h, const KParams& kp)
 {
-    static const bool full = getenv("ABNN_FULL_EXCHANGE") != nullptr;       // measurements only
+    static const bool full = tune_env("ABNN_FULL_EXCHANGE") != nullptr;       // measurements only
     const u64 head = (u64)h->p.n_input + h->p.n_output;
     h->slack_ready = false;
     if (h->p.world_size > 1) {
@@ -329,7 +334,7 @@ int exchange_timestamps(abnn_handle* h, const KParams& kp)
             NC(ncclAllGather(h->d.live + h->lo, h->d.view, h->slice, ncclUint64, h->comm, h->st));
             h->view_stale = false;
         }
-    } else if (h->d.view != h->d.live) {
+    } else if (h->d.view != h->d.live && !kp.use_line32) {      // k_fold32 has already carried the pass's fires into the snapshot
         CU(cudaMemcpyAsync(h->d.view, h->d.live, h->N * sizeof(u64), cudaMemcpyDeviceToDevice, h->st));
     }
     return 0;
@@ -581,12 +586,6 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (dev >= ndev) return fail(ABNN_ERR_INVALID, "device ordinal out of range");
     CU(cudaSetDevice(dev));
 
-    // Random 16-byte gathers and 8-byte timestamp accesses use ONE 32-byte sector each; with the default
-    // L2 fetch granularity every miss pulls 128 B from HBM (measured: 213 B of DRAM reads per event,
-    // profiles/r1_notes.md). Ask for sector-sized fetches (device-wide hint).
-    if (!getenv("ABNN_KEEP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    cudaGetLastError();
-
     abnn_handle* h = new abnn_handle;
     h->p = p; h->device = dev; h->N = N;
     h->slice = (N + p.world_size - 1) / p.world_size;
@@ -623,28 +622,30 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     CUH(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CUH(cudaEventCreate(&h->ev0));
     CUH(cudaEventCreate(&h->ev1));
+    CUH(cudaEventCreate(&h->evj));
     CUH(cudaEventCreate(&h->evk));
     for (int i = 0; i < 8; ++i) CUH(cudaEventCreate(&h->timer[i]));
     for (int i = 0; i < RING; ++i) CUH(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     CUH(cudaMalloc(&h->d_syn, h->cap * sizeof(abnn_synapse)));
     // timestamps in one allocation so that one access-policy window covers the hot arrays, hottest first:
-    //   SNAPSHOT view: [slack32 | visited | live | view]   LIVE view: [live | visited]
-    // slack32 is the per-pass 32-bit form of the snapshot that the line kernel's window gate reads
-    // (traversal.cu:k_build_slack); the 64-bit snapshot `view` serves the other kernels and the read-out.
-    // (Measured: a RED.MAX that misses L2 costs more than a read that misses — with lastVisited outside
-    // the window the pass is 30 % slower. profiles/r1_notes.md)
+    //   SNAPSHOT view: [slack32 | fire32 | vis32 | visited | live | view]   LIVE view: [live | visited]
+    // slack32 / fire32 / vis32 are the per-pass 32-bit forms of the snapshot, lastFired and lastVisited that the line
+    // kernel works on (traversal.cu:k_traverse_line32, k_prepare32, k_fold32): 12 bytes per neuron = 60 MB at 5M neurons,
+    // the size of the persisting-L2 set-aside. The 64-bit arrays serve every other kernel, the read-out and the ABI.
     const u64 npad = (h->npad + 31) & ~31ull;
     const bool snap = p.src_view == ABNN_SRC_SNAPSHOT;
-    const u64 words = snap ? 7 : 4;                          // in units of npad * 4 bytes
+    const u64 words = snap ? 9 : 4;                          // in units of npad * 4 bytes
     CUH(cudaMalloc(&h->d_ts, words * npad * sizeof(u32)));
     CUH(cudaMemsetAsync(h->d_ts, 0, words * npad * sizeof(u32), h->st));                       // brain.cpp:62-64
     if (snap) {
         h->d.slack = reinterpret_cast<u32*>(h->d_ts);
-        h->d.visited = h->d_ts + npad / 2;
+        h->d.fire32 = reinterpret_cast<int*>(h->d.slack + npad);
+        h->d.vis32 = h->d.slack + 2 * npad;
+        h->d.visited = h->d_ts + 3 * npad / 2;
         h->d.live = h->d.visited + npad;
         h->d.view = h->d.live + npad;
     } else {
-        h->d.slack = nullptr;
+        h->d.slack = nullptr; h->d.fire32 = nullptr; h->d.vis32 = nullptr;
         h->d.live = h->d_ts; h->d.view = h->d_ts;
         h->d.visited = h->d_ts + npad;
     }
@@ -677,18 +678,20 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     CUH(cudaMalloc(&h->d_total, 8 * sizeof(u64)));
     CUH(cudaMalloc(&h->d_counts, p.world_size * sizeof(u64)));
 
-    // L2 residency of the timestamp arrays (north star item 2). Tuning knobs (measurements only):
-    // ABNN_L2_ARRAYS = arrays covered by the window, ABNN_L2_MISS = 1 -> lines of the window that do not
-    // get the persisting property are "normal" instead of "streaming".
+    // L2 residency of the timestamp arrays (north star item 2): params.l2_persist = 1 sets aside persisting L2 for the hot
+    // arrays (cudaLimitPersistingL2CacheSize is a DEVICE-wide limit: the handle raises it to what it needs and never lowers
+    // it) and attaches an access-policy window to the handle's stream; l2_persist = 0 touches no device-wide state.
+    // Tuning builds: ABNN_L2_ARRAYS = arrays covered by the window, ABNN_L2_MISS = 1 -> lines of the window that do not get
+    // the persisting property are "normal" instead of "streaming".
     if (p.l2_persist && max_persist > 0 && max_window > 0) {
-        const int n_arr = getenv("ABNN_L2_ARRAYS") ? atoi(getenv("ABNN_L2_ARRAYS")) : 2;
-        const bool miss_normal = getenv("ABNN_L2_MISS") && atoi(getenv("ABNN_L2_MISS")) == 1;
-        // default: slack32 + lastVisited (60 MB at 5M neurons) / LIVE view: lastFired + lastVisited
-        const u64 hot_words = snap ? (n_arr <= 1 ? 1 : n_arr == 2 ? 3 : 5) : (n_arr <= 1 ? 2 : 4);
+        const int n_arr = tune_env("ABNN_L2_ARRAYS") ? atoi(tune_env("ABNN_L2_ARRAYS")) : 3;
+        const bool miss_normal = tune_env("ABNN_L2_MISS") && atoi(tune_env("ABNN_L2_MISS")) == 1;
+        // default: slack32 + fire32 + vis32 (60 MB at 5M neurons) / LIVE view: lastFired + lastVisited
+        const u64 hot_words = snap ? (u64)std::max(1, std::min(n_arr, 9)) : (n_arr <= 1 ? 2 : 4);
         size_t hot = (size_t)hot_words * npad * sizeof(u32);
-        if (getenv("ABNN_L2_EXTRA_MB")) hot += (size_t)atoi(getenv("ABNN_L2_EXTRA_MB")) << 20;   // measurements: reach into the next array
         size_t want = std::min<size_t>(hot, (size_t)max_persist);
-        if (getenv("ABNN_L2_CARVE_MAX")) want = (size_t)max_persist;
+        if (tune_env("ABNN_L2_CARVE_MAX")) want = (size_t)max_persist;
+        { size_t cur = 0; if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur > want) want = cur; }
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             size_t got = 0;
             cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
@@ -696,7 +699,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
             attr.accessPolicyWindow.base_ptr = h->d_ts;
             attr.accessPolicyWindow.num_bytes = std::min<size_t>(hot, (size_t)max_window);
             attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)got / (double)attr.accessPolicyWindow.num_bytes);
-            if (getenv("ABNN_L2_RATIO")) attr.accessPolicyWindow.hitRatio = (float)atof(getenv("ABNN_L2_RATIO"));
+            if (tune_env("ABNN_L2_RATIO")) attr.accessPolicyWindow.hitRatio = (float)atof(tune_env("ABNN_L2_RATIO"));
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = miss_normal ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
             if (cudaStreamSetAttribute(h->st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) h->l2_persist = got;
@@ -733,6 +736,7 @@ void abnn_destroy(abnn_handle* h)
     for (int i = 0; i < RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evj) cudaEventDestroy(h->evj);
     if (h->evk) cudaEventDestroy(h->evk);
     for (int i = 0; i < 8; ++i) if (h->timer[i]) cudaEventDestroy(h->timer[i]);
     if (h->st) cudaStreamDestroy(h->st);
@@ -775,7 +779,7 @@ int abnn_comm_init(abnn_handle* h, const void* id128)
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     NC(ncclCommInitRank(&h->comm, (int)h->p.world_size, id, (int)h->p.rank));
-    if (getenv("ABNN_P2P_EXCHANGE")) RET(p2p_setup(h));     // experiment, not measured yet: peer-memory exchange instead of NCCL
+    if (tune_env("ABNN_P2P_EXCHANGE")) RET(p2p_setup(h));     // experiment, not measured yet: peer-memory exchange instead of NCCL
     return 0;
 }
 
@@ -1162,17 +1166,19 @@ int abnn_get_reward(abnn_handle* h, float* reward, float* rbar)
 
 // Everything one pass enqueues on the handle's stream. Capture-safe for PARALLEL execution (no host
 // synchronisation, no allocation): abnn_engine_step records it into a CUDA graph.
-static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t after_traverse, bool head_refreshed = false)
+static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t before_traverse, cudaEvent_t after_traverse, bool head_refreshed = false)
 {
     if (slack_mode(h, kp)) {
         kp.use_slack = 1;
+        kp.use_line32 = line32_mode(h, kp) ? 1u : 0u;
+        u64 s0 = 0, s1 = h->N;          // gate words to (re)build from the snapshot
         if (h->slack_ready) {           // the exchange delivered the gate words; inject / teacher forcing touched the head since
-            if (!head_refreshed) CU(launch_build_slack(kp, h->d, h->d.view, 0, (u64)h->p.n_input + h->p.n_output, h->st));
-        } else {
-            RET(ensure_view(h));
-            CU(launch_build_slack(kp, h->d, h->d.view, 0, h->N, h->st));
-        }
+            s1 = head_refreshed ? 0 : (u64)h->p.n_input + h->p.n_output;
+        } else RET(ensure_view(h));
+        if (kp.use_line32) CU(launch_prepare32(kp, h->d, h->d.view, s0, s1, h->lo, h->hi, h->st));   // + fire32 / vis32 of the owned neurons
+        else CU(launch_build_slack(kp, h->d, h->d.view, s0, s1, h->st));
     } else RET(ensure_view(h));
+    if (before_traverse) CU(cudaEventRecord(before_traverse, h->st));
     switch (h->p.exec_mode) {
         case ABNN_EXEC_SERIAL:   CU(launch_traverse_serial(kp, h->d, h->st)); break;
         case ABNN_EXEC_PARALLEL: CU(launch_traverse_parallel(kp, h->d, h->sm_count, h->st)); break;
@@ -1180,6 +1186,7 @@ static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t after_traverse, 
     }
     if (after_traverse) CU(cudaEventRecord(after_traverse, h->st));
     CU(launch_end_pass(kp, h->d.sc, h->d_stats, h->st));
+    if (kp.use_line32) CU(launch_fold32(h->d, h->lo, h->hi, h->st));   // the pass's fires / visits back into the 64-bit arrays
     RET(exchange_timestamps(h, kp));
     return 0;
 }
@@ -1190,7 +1197,7 @@ int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
     RET(refresh_counts(h));
     const KParams kp = make_kparams(h, events);
     if (stats) CU(cudaEventRecord(h->ev0, h->st));
-    RET(enqueue_pass(h, kp, stats ? h->evk : nullptr));
+    RET(enqueue_pass(h, kp, stats ? h->evj : nullptr, stats ? h->evk : nullptr));
     if (stats) {
         CU(cudaEventRecord(h->ev1, h->st));
         CU(cudaMemcpyAsync(h->h_pin, h->d_stats, sizeof(abnn_pass_stats), cudaMemcpyDeviceToHost, h->st));
@@ -1199,7 +1206,7 @@ int abnn_run_pass(abnn_handle* h, uint64_t events, abnn_pass_stats* stats)
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         stats->device_ms = ms;
-        CU(cudaEventElapsedTime(&ms, h->ev0, h->evk));
+        CU(cudaEventElapsedTime(&ms, h->evj, h->evk));
         stats->traverse_ms = ms;
     }
     return 0;
@@ -1221,7 +1228,7 @@ static int enqueue_step(abnn_handle* h, const KParams& kp)
     const u32 ni = h->p.n_input, no = h->p.n_output;
     const bool refresh = slack_mode(h, kp) && h->slack_ready;
     CU(launch_step_prologue(kp, h->d, h->d_frame, ni, no, h->p.teacher_gap, refresh, h->st));
-    RET(enqueue_pass(h, kp, nullptr, refresh));
+    RET(enqueue_pass(h, kp, nullptr, nullptr, refresh));
     CU(launch_readout(kp, h->d, readout_params(h), h->rs, h->d_frame + ni, h->st));
     return 0;
 }
@@ -1250,15 +1257,15 @@ int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, flo
     CU(cudaEventRecord(h->frame_ev[slot], h->st));
 
     const KParams kp = make_kparams(h, events);
-    static const bool no_graph = getenv("ABNN_NO_GRAPH") != nullptr;
+    static const bool no_graph = tune_env("ABNN_NO_GRAPH") != nullptr;
     // Single-GPU handles only: with the NCCL exchange inside the captured sequence a 2-rank run hung in
     // this environment (NCCL 2.28.9, driver 580); sharded handles enqueue the same sequence eagerly.
     // With the peer-memory exchange (p2p_setup) the sharded sequence holds no NCCL call once the gate words are being
     // exchanged (slack_ready), so it can be captured too: opt-in on top of ABNN_P2P_EXCHANGE, not measured yet.
-    static const bool p2p_graph = getenv("ABNN_P2P_GRAPH") != nullptr;
+    static const bool p2p_graph = tune_env("ABNN_P2P_GRAPH") != nullptr;
     const bool pre[2] = {h->slack_ready, h->view_stale};
     const bool sharded_ok = p2p_graph && h->p2p && pre[0] && slack_mode(h, kp) && h->slice >= (u64)h->p.n_input + h->p.n_output &&
-                            !getenv("ABNN_FULL_EXCHANGE");
+                            !tune_env("ABNN_FULL_EXCHANGE");
     const bool capturable = h->p.exec_mode == ABNN_EXEC_PARALLEL && (h->p.world_size == 1 || sharded_ok) && !no_graph;
     const bool match = h->step_exec && h->step_events == events && h->step_counts == h->n_local_all &&
                        h->step_pre[0] == pre[0] && h->step_pre[1] == pre[1];
@@ -1433,8 +1440,8 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
     abnn_structural_stats s{};
     s.n_before = h->n_local;
     const bool prune = h->p.w_prune > 0.f && h->n_local, grow = h->p.p_new > 0.f;
-    static const bool resort = getenv("ABNN_GROW_RESORT") != nullptr;      // measurements: full radix re-sort instead of the merge
-    static const bool no_fuse = getenv("ABNN_NO_FUSED_PRUNE") != nullptr;  // measurements: prune and merge as two passes
+    static const bool resort = tune_env("ABNN_GROW_RESORT") != nullptr;      // measurements: full radix re-sort instead of the merge
+    static const bool no_fuse = tune_env("ABNN_NO_FUSED_PRUNE") != nullptr;  // measurements: prune and merge as two passes
     // growth candidates first (they do not depend on the table): their number decides how the table is rewritten
     GrowCand* list = nullptr;
     u32 owned = 0;
@@ -1449,7 +1456,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
         // 1. prune: stable compaction — into the spare table (count pass + scatter pass, no chained scan) when there is
         //    memory for one, else in place (k_compact)
         if (prune) {
-            static const bool in_place_only = getenv("ABNN_PRUNE_IN_PLACE") != nullptr;   // measurements only
+            static const bool in_place_only = tune_env("ABNN_PRUNE_IN_PLACE") != nullptr;   // measurements only
             const bool two_tables = 2 * h->cap * sizeof(abnn_synapse) <= h->mem_total / 2;
             abnn_synapse* spare = nullptr;
             if (!in_place_only && (h->d_spare || two_tables)) {

@@ -3,6 +3,7 @@
 // sequence of IEEE single-precision operations as the reference kernel (brain.metal:91-121).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/abnn.h"
@@ -11,6 +12,15 @@ namespace abnn {
 
 typedef unsigned long long u64;
 typedef unsigned int       u32;
+
+// Measurement knobs (environment variables that switch experimental code paths) exist only in tuning builds
+// (nvcc -DABNN_TUNING, e.g. ABNN_NVCC_EXTRA=-DABNN_TUNING python -m abnn_b200.build): the product library reads no
+// environment variable — everything that changes its behaviour is a field of abnn_params.
+#ifdef ABNN_TUNING
+inline const char* tune_env(const char* name) { return getenv(name); }
+#else
+inline const char* tune_env(const char*) { return nullptr; }
+#endif
 
 // Philox counter layout: ctr = (idx.lo, idx.hi, aux, stream), key = seed.
 enum : u32 { STREAM_EVENT = 0, STREAM_GROW = 1, STREAM_INJECT = 2, STREAM_TEACHER = 3, STREAM_INIT = 4 };
@@ -75,6 +85,25 @@ __host__ __device__ __forceinline__ u32 slack_word(u64 clock, u64 last_fired, u6
     return room >= 0xFFFFFFFDull ? 0xFFFFFFFEu : (u32)room + 1u;
 }
 
+// 32-bit pass-relative timestamps of the line kernel (traversal.cu:k_traverse_line32). For the pass that starts at
+// `clock`, fire32[n] = lastFired[n] - clock as a signed word (<= 0: fired before the pass, >= 0: tick offset of a fire of
+// this pass; moved with 32-bit atomicMax) and vis32[n] = 1 + the latest tick offset at which n was visited in this pass
+// (0 = not visited). Both are rebuilt from / folded back into the 64-bit arrays around every pass (k_prepare32 /
+// k_fold32), so nothing outside the line kernel sees them. Magnitudes are kept below 2^30; the two sentinels mean
+// "further away than that": the rare event that needs the exact value reads the 64-bit array.
+constexpr int FIRE32_LIMIT = 1 << 30;
+constexpr int FIRE32_ANCIENT = -FIRE32_LIMIT;        // lastFired <= clock - 2^30
+constexpr int FIRE32_FUTURE = FIRE32_LIMIT - 1;      // lastFired >= clock + 2^30 - 1 (only after an upload of future timestamps)
+__host__ __device__ __forceinline__ int fire_word(u64 clock, u64 last_fired)
+{
+    if (last_fired <= clock) {
+        const u64 age = clock - last_fired;
+        return age >= (u64)FIRE32_LIMIT ? FIRE32_ANCIENT : -(int)age;
+    }
+    const u64 ahead = last_fired - clock;
+    return ahead >= (u64)FIRE32_FUTURE ? FIRE32_FUTURE : (int)ahead;
+}
+
 // Growth candidate staged by a firing event; appended in `order` by the structural step.
 struct GrowCand { u64 order; u32 src, dst; };
 
@@ -126,6 +155,7 @@ struct KParams {
     float base_scale, a_ltp, a_ltd, w_min, w_max, eta_home, target_rate_hz, home_tick_hz, eta_reward, alpha_rbar;
     float p_new;
     u32 use_slack;       // the line kernel reads DevPtrs::slack instead of the 64-bit snapshot
+    u32 use_line32;      // k_traverse_line32 runs this pass (32-bit pass-relative timestamps)
 };
 
 struct DevPtrs {
@@ -134,6 +164,8 @@ struct DevPtrs {
     u64* live;           // lastFired, authoritative for the owned dst range (indexed by global id)
     u64* visited;        // lastVisited
     u32* slack;          // per-pass 32-bit form of the snapshot for the pre-spike window gate (line kernel), or null
+    int* fire32;         // per-pass 32-bit form of lastFired of the owned neurons (k_traverse_line32), or null
+    u32* vis32;          // per-pass 32-bit form of lastVisited (k_traverse_line32), or null
     DevScalars* sc;
     GrowCand* grow;
 };

@@ -10,6 +10,12 @@ cudaError_t launch_traverse_serial(const KParams& kp, const DevPtrs& d, cudaStre
 // slack[n], n in [n0, n1), from lastFired values src[n] for the pass that starts at sc->clock (see k_build_slack)
 cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* src, u64 n0, u64 n1, cudaStream_t st);
 bool line_kernel_selected(const KParams& kp);
+// k_traverse_line32 (32-bit pass-relative timestamps): can it run this pass / conversions around the pass
+bool line32_selected(const KParams& kp);
+// gate words of [s0,s1) from the snapshot `src`, fire32 / vis32 of the owned neurons [o0,o1) from the 64-bit lastFired
+cudaError_t launch_prepare32(const KParams& kp, const DevPtrs& d, const u64* src, u64 s0, u64 s1, u64 o0, u64 o1, cudaStream_t st);
+// fires and visits of the pass back into lastFired / snapshot / lastVisited of [o0,o1); runs after k_end_pass
+cudaError_t launch_fold32(const DevPtrs& d, u64 o0, u64 o1, cudaStream_t st);
 cudaError_t launch_end_pass(const KParams& kp, DevScalars* sc, abnn_pass_stats* out, cudaStream_t st);
 
 // exchange.cu — the per-pass exchange of a sharded PARALLEL run as peer-memory stores (opt-in, see capi.cu:p2p_setup)

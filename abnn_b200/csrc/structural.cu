@@ -376,7 +376,7 @@ cudaError_t launch_prune_merge_sorted(const abnn_synapse* syn, u64 n, float w_pr
     CompactArgs a{};
     a.in = syn; a.out = out; a.n = n; a.out_cap = out_cap; a.pred = KEEP_NOT_PRUNED; a.w_prune = w_prune;
     a.shift = cnt; a.shift_lo = dst_lo; a.drop_hist = pruned;
-    static const bool lookback = getenv("ABNN_COMPACT_LOOKBACK") != nullptr;     // measurements: the single-pass chained scan
+    static const bool lookback = tune_env("ABNN_COMPACT_LOOKBACK") != nullptr;     // measurements: the single-pass chained scan
     e = lookback ? launch_compact(a, compact_scratch, d_total, st) : launch_compact_two_pass(a, compact_scratch, d_total, st);
     if (e != cudaSuccess) return e;
     e = cub::DeviceScan::InclusiveSum(scan_tmp, scan_tmp_bytes, pruned, pruned, (long long)dst_span + 2, st);

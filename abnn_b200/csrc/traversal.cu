@@ -685,6 +685,299 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
 }
 
+// ================================================================================================
+// k_traverse_line32 — the line sampler on 32-bit pass-relative timestamps (what bench.py times).
+//
+// Same walk as k_traverse_line (a warp copies chunks of 32 Philox-chosen 128-byte lines into its 4 KB stage, gate
+// reads in flight, refractory prefilter, compaction, dense steps), but every time in the kernel is a 32-bit tick
+// offset from the pass-start clock:
+//   slack32[src]  pre-spike gate word (k_build_slack)                      20 MB at 5M neurons
+//   fire32[dst]   lastFired - clock, signed, moved with atomicMax.s32       20 MB
+//   vis32[dst]    1 + latest visit offset of the pass, RED.MAX.U32         20 MB
+// 60 MB = exactly the persisting-L2 carve-out, so the three arrays every event touches stay resident under the 16 GB
+// stream and the only DRAM traffic left is the table itself (the 64-bit lastFired array cost one 128-byte DRAM line per
+// miss — as much as the table line of the event that caused it; profiles/r2_notes.md). k_prepare32 / k_fold32 convert
+// from / to the 64-bit arrays around the pass.
+// Preconditions (launch_traverse_parallel checks them, else k_traverse_line runs): per-event clock, no spike budget,
+// snapshot src view with gate words, ticks of the pass < 2^30 - 1, refractory < 2^30, and refractory >= the tick span of
+// one chunk (256 * world). The last one makes the in-warp ordering a one-round affair: inside a chunk, the first event
+// of a destination that fires blocks every later event of that destination (they are within the refractory period of
+// its tick), events before it keep the decision they took against memory — exactly what chain_resolve iterates to.
+// One Philox call per line: .x.y choose the line, .z/.w carry the release / growth words of its 8 events
+// (common.cuh:release_word).
+// SB = sample_block: 8 (one 128-byte line per draw) or 16 (two consecutive lines = 256 bytes per draw, the size at which
+// random HBM3e reads reach the copy bandwidth: 6.7 TB/s against 4.7 TB/s for single lines, profiles/r2_notes.md).
+template <int VISITS, int GROW, int SB>
+__global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_traverse_line32(const __grid_constant__ KParams kp, const DevPtrs d)
+{
+    constexpr int LOGB = 3, B = 8, PART = ABNN_LINE_PART;     // a LINE is 8 records; a sample group is LPG lines
+    constexpr int LPG = SB / 8, LOGSB = SB == 8 ? 3 : 4, GPC = 32 / LPG;
+    static_assert(SB == 8 || SB == 16, "line kernel: sample_block 8 or 16");
+    extern __shared__ __align__(128) unsigned char line_smem[];
+    __shared__ u32 s_cnt[3];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = line_smem + warp * LINE_WARP_SMEM;
+    unsigned char* queue = stage + LINE_STAGE_BYTES;
+    u32* fl_dst = reinterpret_cast<u32*>(queue + 256);             // destinations that fired in this chunk
+    const unsigned char* mine = stage + lane * 16;
+    const u32 mine_addr = (u32)__cvta_generic_to_shared(mine);
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 clock = d.sc->clock, event_base = d.sc->event_base, tick_base = d.sc->tick_base;
+    const float R = d.sc->reward, rbar = d.sc->rbar;
+    u32 n_cand = 0, n_gated = 0, n_fired = 0;
+    const u32 rec = lane & (B - 1), sub = lane >> LOGB;
+    const unsigned lt = (1u << lane) - 1u;
+    const u32 count = (u32)kp.count;                               // < 2^30 (ticks < 2^30)
+    const u32 n_chunks = (count + 32u * B - 1) / (32u * B);
+    const u32 world = kp.world, refr = (u32)kp.refractory;
+
+    // lane L holds LINE L of chunk c: m = line base (a multiple of 8) | (valid records - 1), ~0 = none; zw = .z | .w << 32 of
+    // the Philox call of the line's sample group (release / growth words of its events). With two lines per group both
+    // lanes of a group evaluate the group's draw (same warp instructions, no shuffle).
+    u64 zw = 0, zw_next = 0;
+    auto draw = [&](u32 c, u64& zw_out) -> u64 {
+        const u32 i0 = (c * GPC + (lane / LPG)) << LOGSB;    // first event of the line's group
+        if (c >= n_chunks || i0 >= count) return ~0ull;
+        const Philox4 r = event_philox(kp, event_base + i0);
+        zw_out = (u64)r.z | ((u64)r.w << 32);
+        const u64 be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGSB;
+        u64 valid = kp.n_local - be;                         // the table's last block may be short,
+        if (count - i0 < valid) valid = count - i0;          // and so may the pass's last group
+        const u32 off = (lane % LPG) * B;                    // this line's records inside the group
+        if (valid <= off) return ~0ull;
+        valid -= off;
+        return (be + off) | ((valid < B ? valid : B) - 1);
+    };
+    const u32 warps_total = gridDim.x * LINE_WARPS, warp_global = blockIdx.x * LINE_WARPS + warp;
+    const u32 static_rounds = (n_chunks / warps_total) * 13 / 16;
+    u32 round = 0;
+    auto take = [&]() -> u32 {
+        if (round < static_rounds) return warp_global + (round++) * warps_total;
+        u32 t = 0;
+        if (lane == 0) t = atomicAdd(&d.sc->chunk_ticket, 1u);
+        return static_rounds * warps_total + __shfl_sync(0xffffffffu, t, 0);
+    };
+    u32 c = take();
+    u64 m = draw(c, zw);
+    while (c < n_chunks) {
+        // ---- stage the chunk ------------------------------------------------------------------------
+        u32 okm = 0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const u64 mk = __shfl_sync(0xffffffffu, m, k * 4 + sub);
+            if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u)) {
+                okm |= 1u << k;
+                cp_async16(mine_addr + k * 512, d.syn + (mk & ~7ull) + rec);
+            }
+        }
+        cp_async_commit();
+        // two groups of the chunk drew the same line (small tables only): the later one re-reads the weights
+        const unsigned same = __match_any_sync(0xffffffffu, m);
+        const unsigned dupm = __ballot_sync(0xffffffffu, m != ~0ull && (same & lt) != 0);
+        const u32 c_next = take();
+        const u64 m_next = draw(c_next, zw_next);            // ALU work under the copy's latency
+        const u32 ev0 = c * (32u * B);                       // first event of the chunk (local index)
+        const u32 t0 = ev0 * world + kp.rank;                // its tick offset: now = clock + t
+        cp_async_wait<0>();
+        __syncwarp();
+
+        // ---- A + B: gate words and fire32[dst] in flight, window test, visit, refractory prefilter, compaction ----
+        u32 candm = 0, nC = 0;
+#pragma unroll
+        for (int k0 = 0; k0 < B; k0 += PART) {
+            u32 gate[PART];
+            int fire[PART];
+            u32 exact = 0;
+#pragma unroll
+            for (int j = 0; j < PART; ++j) {
+                const int k = k0 + j;
+                gate[j] = 0; fire[j] = 0;
+                if ((okm >> k) & 1u) {
+                    const uint2 sd = *reinterpret_cast<const uint2*>(mine + k * 512);
+                    gate[j] = __ldcg(d.slack + sd.x);                                       // brain.metal:73 (32-bit form)
+                    fire[j] = __ldcg(d.fire32 + sd.y);                                      // brain.metal:79 (32-bit form)
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PART; ++j) {
+                const int k = k0 + j;
+                candm |= (u32)(((okm >> k) & 1u) && t0 + (k * 32 + lane) * world < gate[j]) << k;   // brain.metal:74
+                exact |= (u32)(gate[j] == SLACK_EXACT) << k;
+            }
+            if (__any_sync(0xffffffffu, exact & okm)) {      // snapshot in the future of the pass start: exact 64-bit test
+#pragma unroll
+                for (int j = 0; j < PART; ++j) {
+                    const int k = k0 + j;
+                    if (((exact & okm) >> k) & 1u) {
+                        const u64 now = clock + t0 + (k * 32 + lane) * world;
+                        const bool cand = now - __ldcg(d.view + *reinterpret_cast<const u32*>(mine + k * 512)) <= kp.window_pre;
+                        candm = (candm & ~(1u << k)) | ((u32)cand << k);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PART; ++j) {
+                const int k = k0 + j;
+                const u32 t = t0 + (k * 32 + lane) * world;
+                const bool ok = (okm >> k) & 1u;
+                if (VISITS) {                                                               // README.md:84, once per run of equal dst
+                    const u32 key = ok ? *reinterpret_cast<const u32*>(mine + k * 512 + 4) : 0xFFFFFFFFu;
+                    const u32 next = __shfl_down_sync(0xffffffffu, key, 1);
+                    if (ok && (lane == 31 || next != key)) atomicMax(d.vis32 + key, t + 1u);
+                }
+                const int gap = (int)t - fire[j];                                           // |gap| < 2^31
+                const bool open = ((candm >> k) & 1u) && (u32)(gap < 0 ? -gap : gap) > refr;   // brain.metal:79-83
+                const unsigned cm = __ballot_sync(0xffffffffu, open);
+                if (open) queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
+                nC += __popc(cm);
+            }
+        }
+        n_cand += __popc(candm);
+        __syncwarp();
+
+        // ---- C: dense steps over the queue ----------------------------------------------------------------
+        u32 nf = 0;                                          // destinations that fired in this chunk so far (warp-uniform)
+        bool spilled = false;
+        u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0); int fv = 0;
+        bool cand = lane < nC;
+        if (cand) {
+            le = queue[lane];
+            sy = *reinterpret_cast<const uint4*>(stage + le * 16);                          // brain.metal:70
+            fv = __ldcg(d.fire32 + sy.y);                                                   // brain.metal:79
+        }
+        u32 j = 0;
+#pragma unroll 1
+        while (j < nC) {
+            u32 le_n = 0; uint4 sy_n = make_uint4(0, 0, 0, 0); int fv_n = 0;
+            const bool cand_n = j + 32 + lane < nC;
+            if (cand_n) {                                    // next step's record and fire32[dst] on their way
+                le_n = queue[j + 32 + lane];
+                sy_n = *reinterpret_cast<const uint4*>(stage + le_n * 16);
+                fv_n = __ldcg(d.fire32 + sy_n.y);
+            }
+            const u32 g = le >> LOGB, r8 = le & 7u;
+            const u64 edge = (__shfl_sync(0xffffffffu, m, g) & ~7ull) + r8;
+            const u64 zwg = __shfl_sync(0xffffffffu, zw, g);
+            const u32 t = t0 + le * world;
+            u32 adv = 32;
+            if (dupm) {
+                // Two groups of this chunk drew the same line (tables of a few hundred lines only). Their events must not
+                // share a dense step — the later one has to see the weight the earlier one wrote — so the step is cut
+                // in front of the first lane whose line already appears in it under another group; the rest is redone.
+                const unsigned cm0 = __ballot_sync(0xffffffffu, cand);
+                unsigned pe = 1u << lane;
+                if (cand) pe = __match_any_sync(cm0, (u32)(edge >> LOGB));
+                const u32 g_first = __shfl_sync(0xffffffffu, g, __ffs(pe) - 1);
+                const unsigned cut = __ballot_sync(0xffffffffu, cand && g != g_first);
+                if (cut) { adv = __ffs(cut) - 1; cand = cand && lane < adv; }
+            }
+            float w = __uint_as_float(sy.z);
+            bool skip = true, want = false;
+            int gap = 0;
+            if (cand) {
+                if ((dupm >> g) & 1u) w = __ldcg(&d.syn[edge].w);
+                if (spilled) fv = __ldcg(d.fire32 + sy.y);
+                gap = (int)t - fv;
+                skip = (u32)(gap < 0 ? -gap : gap) <= refr;                                 // brain.metal:79-83
+                if (!spilled)
+                    for (u32 f = 0; f < nf; ++f) skip = skip || fl_dst[f] == sy.y;          // fired earlier in this chunk: refractory
+                const float u = kp.release_rng == ABNN_RNG_XORSHIFT ? rand01_xorshift((ev0 + le) ^ (u32)(clock + t))
+                                                                    : u01_24(release_word((u32)zwg, SB, (g % LPG) * B + r8));
+                want = !skip && release_test(kp, w, u);                                     // brain.metal:91-92
+            }
+            // in-warp order: the first event of a destination that fires blocks its later events (see header)
+            const unsigned cmask = __ballot_sync(0xffffffffu, cand);
+            const unsigned wm = __ballot_sync(0xffffffffu, want);
+            bool fired = false, gated = false;
+            if (cand) {
+                const unsigned F = wm & __match_any_sync(cmask, sy.y);
+                const int first = F ? __ffs(F) - 1 : 32;
+                fired = want && (int)lane == first;
+                gated = !skip && (int)lane <= first;
+            }
+            if (gated) {
+                u64 isi = (u64)(u32)(gap < 0 ? -gap : gap);
+                if (fv == FIRE32_ANCIENT || fv == FIRE32_FUTURE) {   // beyond 2^30 ticks: the exact inter-spike interval
+                    const u64 ld = __ldcg(d.live + sy.y), now = clock + t;
+                    isi = ld <= now ? now - ld : ld - now;
+                }
+                __stcg(&d.syn[edge].w, plasticity(kp, w, fired, R, rbar, isi));             // brain.metal:101-122
+            }
+            if (fired) {
+                atomicMax(d.fire32 + sy.y, (int)t);                                         // brain.metal:125-126
+                if (GROW) stage_growth(kp, d, event_base + ev0 + le, tick_base + t, sy.x, trial_word((u32)(zwg >> 32), SB, (g % LPG) * B + r8));
+            }
+            n_gated += gated; n_fired += fired;
+            const unsigned fm = __ballot_sync(0xffffffffu, fired);
+            if (fm) {
+                const u32 at = nf + __popc(fm & lt);
+                if (fired && at < LINE_FIRE_CAP) fl_dst[at] = sy.y;
+                nf += __popc(fm);
+                if (nf > LINE_FIRE_CAP) { nf = LINE_FIRE_CAP; spilled = true; }
+                __syncwarp();
+            }
+            if (dupm | (u32)spilled) __threadfence();        // rare: make this step's writes visible to the re-reads
+            j += adv;
+            if (adv == 32) { cand = cand_n; le = le_n; sy = sy_n; fv = fv_n; }
+            else {                                           // a cut step: take up again behind it
+                cand = j + lane < nC;
+                if (cand) {
+                    le = queue[j + lane];
+                    sy = *reinterpret_cast<const uint4*>(stage + le * 16);
+                    fv = __ldcg(d.fire32 + sy.y);
+                }
+            }
+        }
+        __syncwarp();                                        // every lane is done with the stage
+        c = c_next; m = m_next; zw = zw_next;
+    }
+    flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
+}
+
+// Before the pass: gate words of neurons [s0, s1) from the snapshot `src` (as k_build_slack), fire32 / vis32 of the owned
+// neurons [o0, o1) from the 64-bit lastFired.
+__global__ void __launch_bounds__(256) k_prepare32(const __grid_constant__ KParams kp, const DevPtrs d, const u64* src, u64 s0, u64 s1,
+                                                   u64 o0, u64 o1)
+{
+    const u64 clock = d.sc->clock;
+    const u64 step = (u64)gridDim.x * blockDim.x, tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (u64 n = s0 + tid; n < s1; n += step) d.slack[n] = slack_word(clock, src[n], kp.window_pre);
+    for (u64 n = o0 + tid; n < o1; n += step) { d.fire32[n] = fire_word(clock, d.live[n]); d.vis32[n] = 0u; }
+}
+// After the pass (k_end_pass has advanced the clock): fires and visits of the pass back into the 64-bit arrays. A
+// non-negative fire32 is lastFired - pass start (a fire of this pass, or an uploaded future timestamp that no fire
+// overtook — the same value it already has); the snapshot entry follows (single GPU: snapshot == lastFired between passes).
+__global__ void __launch_bounds__(256) k_fold32(const DevPtrs d, u64 o0, u64 o1)
+{
+    const u64 start = d.sc->clock - d.sc->last_pass_ticks;
+    for (u64 n = o0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; n < o1; n += (u64)gridDim.x * blockDim.x) {
+        const int f = d.fire32[n];
+        if (f >= 0 && f != FIRE32_FUTURE) { d.live[n] = start + (u32)f; d.view[n] = start + (u32)f; }
+        const u32 v = d.vis32[n];
+        if (v) { const u64 tv = start + v - 1u; if (d.visited[n] < tv) d.visited[n] = tv; }
+    }
+}
+cudaError_t launch_prepare32(const KParams& kp, const DevPtrs& d, const u64* src, u64 s0, u64 s1, u64 o0, u64 o1, cudaStream_t st)
+{
+    if (s1 < s0) s1 = s0;
+    if (o1 < o0) o1 = o0;
+    const u64 span = s1 - s0 > o1 - o0 ? s1 - s0 : o1 - o0;
+    if (!span) return cudaSuccess;
+    u64 blocks = (span + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prepare32<<<(unsigned)blocks, 256, 0, st>>>(kp, d, src, s0, s1, o0, o1);
+    return cudaGetLastError();
+}
+cudaError_t launch_fold32(const DevPtrs& d, u64 o0, u64 o1, cudaStream_t st)
+{
+    if (o1 <= o0) return cudaSuccess;
+    u64 blocks = (o1 - o0 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_fold32<<<(unsigned)blocks, 256, 0, st>>>(d, o0, o1);
+    return cudaGetLastError();
+}
+
 // End of pass: r-bar EWMA (once per pass), clock (brain.metal:129 / README.md:85),
 // counters into the stats slot, counters reset for the next pass.
 __global__ void k_end_pass(const __grid_constant__ KParams kp, DevScalars* sc, abnn_pass_stats* out)
@@ -723,8 +1016,8 @@ template <int SAMPLER, int VISITS>
 static cudaError_t launch_parallel_t(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     // tuning knobs (read once): events in flight per thread, CTAs per SM
-    static const int u = getenv("ABNN_TRAV_U") ? atoi(getenv("ABNN_TRAV_U")) : 4;
-    static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
+    static const int u = tune_env("ABNN_TRAV_U") ? atoi(tune_env("ABNN_TRAV_U")) : 4;
+    static const int bps = tune_env("ABNN_TRAV_CTAS") ? atoi(tune_env("ABNN_TRAV_CTAS")) : 0;
     switch (u) {
         case 1:  return launch_parallel_u<SAMPLER, VISITS, 1>(kp, d, sm_count, bps, st);
         case 2:  return launch_parallel_u<SAMPLER, VISITS, 2>(kp, d, sm_count, bps, st);
@@ -737,7 +1030,7 @@ static cudaError_t launch_parallel_t(const KParams& kp, const DevPtrs& d, int sm
 template <int VISITS, int SLACK>
 static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
-    static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
+    static const int bps = tune_env("ABNN_TRAV_CTAS") ? atoi(tune_env("ABNN_TRAV_CTAS")) : 0;
     // function attributes are per device: one process may own handles on several GPUs
     static bool configured[64] = {};
     int dev = 0;
@@ -745,8 +1038,8 @@ static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
         if (e != cudaSuccess) return e;
-        if (getenv("ABNN_LINE_CARVEOUT"))      // measurements only: shared-memory share of the L1/shared array, percent
-            cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("ABNN_LINE_CARVEOUT")));
+        if (tune_env("ABNN_LINE_CARVEOUT"))      // measurements only: shared-memory share of the L1/shared array, percent
+            cudaFuncSetAttribute(k_traverse_line<VISITS, SLACK>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(tune_env("ABNN_LINE_CARVEOUT")));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     if (!kp.count || !kp.n_local) return cudaSuccess;
@@ -772,10 +1065,36 @@ static cudaError_t launch_line(const KParams& kp, const DevPtrs& d, int sm_count
     return cudaGetLastError();
 }
 
+template <int VISITS, int GROW, int SB>
+static cudaError_t launch_line32(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
+{
+    static bool configured[64] = {};                         // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_traverse_line32<VISITS, GROW, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    if (!kp.count || !kp.n_local) return cudaSuccess;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line32<VISITS, GROW, SB>, LINE_WARPS * 32, LINE_SMEM);
+    if (per_sm < 1) per_sm = 1;
+    const u64 chunks = (kp.count + 255) / 256;
+    u64 grid = (u64)sm_count * per_sm;
+    if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
+    // events in flight at once execute unordered: keep that window below a quarter of the refractory period (launch_line)
+    u64 lim = kp.refractory / (256ull * kp.world) / (4 * LINE_WARPS);
+    if (lim < 1) lim = 1;
+    if (grid > lim) grid = lim;
+    k_traverse_line32<VISITS, GROW, SB><<<(unsigned)grid, LINE_WARPS * 32, LINE_SMEM, st>>>(kp, d);
+    return cudaGetLastError();
+}
+
 template <int LOGB, int VISITS>
 static cudaError_t launch_block_t(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
-    static const int bps = getenv("ABNN_TRAV_CTAS") ? atoi(getenv("ABNN_TRAV_CTAS")) : 0;
+    static const int bps = tune_env("ABNN_TRAV_CTAS") ? atoi(tune_env("ABNN_TRAV_CTAS")) : 0;
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_block<LOGB, VISITS>, 256, 0);
     if (per_sm < 1) per_sm = 1;
@@ -802,12 +1121,28 @@ static cudaError_t launch_block(const KParams& kp, const DevPtrs& d, int sm_coun
 
 bool line_kernel_selected(const KParams& kp)
 {
-    static const bool legacy_block = getenv("ABNN_TRAV_LEGACY_BLOCK") != nullptr;      // A/B measurements only
+    static const bool legacy_block = tune_env("ABNN_TRAV_LEGACY_BLOCK") != nullptr;      // A/B measurements only
     return kp.sampler == ABNN_SAMPLER_PHILOX && kp.sample_block == 8 && !legacy_block;
+}
+// k_traverse_line32's preconditions (see its header); the caller additionally needs the gate words (slack_mode)
+bool line32_selected(const KParams& kp)
+{
+    const u64 lim = 1ull << 30;
+    return kp.sampler == ABNN_SAMPLER_PHILOX && (kp.sample_block == 8 || kp.sample_block == 16) && kp.clock_mode == ABNN_CLOCK_PER_EVENT && !kp.budget_on && kp.snapshot &&
+           kp.ticks < lim - 1 && kp.refractory < lim && kp.refractory >= 256ull * kp.world;
 }
 cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     const bool ph = kp.sampler == ABNN_SAMPLER_PHILOX, vis = kp.track_visits != 0;
+    if (kp.use_line32) {
+        const bool grow = kp.p_new > 0.f;
+        if (kp.sample_block == 16) {
+            if (vis) return grow ? launch_line32<1, 1, 16>(kp, d, sm_count, st) : launch_line32<1, 0, 16>(kp, d, sm_count, st);
+            return grow ? launch_line32<0, 1, 16>(kp, d, sm_count, st) : launch_line32<0, 0, 16>(kp, d, sm_count, st);
+        }
+        if (vis) return grow ? launch_line32<1, 1, 8>(kp, d, sm_count, st) : launch_line32<1, 0, 8>(kp, d, sm_count, st);
+        return grow ? launch_line32<0, 1, 8>(kp, d, sm_count, st) : launch_line32<0, 0, 8>(kp, d, sm_count, st);
+    }
     if (line_kernel_selected(kp)) {
         if (kp.use_slack) return vis ? launch_line<1, 1>(kp, d, sm_count, st) : launch_line<0, 1>(kp, d, sm_count, st);
         return vis ? launch_line<1, 0>(kp, d, sm_count, st) : launch_line<0, 0>(kp, d, sm_count, st);

@@ -46,6 +46,29 @@ template <int U> __global__ void __launch_bounds__(256) k_line_regs(Arrays a, u6
     if (acc == 0x12345678u) *sink = acc;
 }
 
+// L0b: random blocks of BL consecutive 128-byte lines (sample_block = 8*BL records per draw): DRAM page locality vs block size
+template <int BL> __global__ void __launch_bounds__(256) k_block_regs(Arrays a, u64 n_chunks, unsigned* sink)
+{
+    const u32 lane = threadIdx.x & 31, rec = lane & 7, sub = lane >> 3;
+    const u64 warps = (u64)gridDim.x * 8, w = (u64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    unsigned acc = 0;
+    for (u64 c = w; c < n_chunks; c += warps) {
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            uint4 r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u64 idx = c * 32 + (k0 + k) * 4 + sub;                 // line ordinal of the pass
+                const u64 blk = __umul64hi(mix((idx / BL) * 0x9E3779B97F4A7C15ULL + 1), a.n_lines / BL);
+                r[k] = __ldcg(a.tab + (blk * BL + idx % BL) * 8 + rec);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc += r[k].x ^ r[k].w;
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
 // L1..L4: the kernel's structure — 8 warps per CTA, one 4 KB stage per warp, 8 cp.async per lane per chunk
 template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arrays a, u64 n_chunks, unsigned* sink)
 {
@@ -132,8 +155,8 @@ int main(int argc, char** argv)
     a.gate = reinterpret_cast<u32*>(hot); a.visited = reinterpret_cast<u64*>(hot + npad * 4); a.live = a.visited + npad;
     // second layout: [gate 4 B | dstw {vis32, fire32} 8 B] per neuron = 60 MB, and [gate | fire32 | vis32]
     unsigned char* hot2; CK(cudaMalloc(&hot2, npad * 12)); CK(cudaMemset(hot2, 0, npad * 12));
-    u32* gate2 = reinterpret_cast<u32*>(hot2);
-    a.dstw = reinterpret_cast<uint2*>(hot2 + npad * 4); a.fire32 = reinterpret_cast<u32*>(hot2 + npad * 4); a.vis32 = a.fire32 + npad;
+    u32* gate2 = reinterpret_cast<u32*>(hot2 + npad * 8);
+    a.dstw = reinterpret_cast<uint2*>(hot2); a.fire32 = reinterpret_cast<u32*>(hot2); a.vis32 = a.fire32 + npad;
     unsigned* sink; CK(cudaMalloc(&sink, 4));
     cudaStream_t st; CK(cudaStreamCreate(&st));
     CK(cudaFuncSetAttribute(k_line_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
@@ -150,6 +173,10 @@ int main(int argc, char** argv)
     report("L0 line reads into registers, 2 x 4 lines in flight per warp", timeit([&] { k_line_regs<2><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     report("L0 line reads into registers, 4 x 4 lines in flight per warp", timeit([&] { k_line_regs<4><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     report("L0 line reads into registers, 8 x 4 lines in flight per warp", timeit([&] { k_line_regs<8><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
+    report("L0b blocks of 2 lines (256 B) per draw", timeit([&] { k_block_regs<2><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
+    report("L0b blocks of 4 lines (512 B) per draw", timeit([&] { k_block_regs<4><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
+    report("L0b blocks of 8 lines (1 KB) per draw", timeit([&] { k_block_regs<8><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
+    report("L0b blocks of 32 lines (4 KB) per draw", timeit([&] { k_block_regs<32><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     for (int window = 0; window < 2; ++window) {
         if (window) {                       // persisting window over [gate | visited] = 12 B per neuron, like the product
             int max_persist = 0, max_window = 0;
@@ -174,9 +201,21 @@ int main(int argc, char** argv)
     }
     // ---- packed 32-bit destination words: [gate | {vis32, fire32}] = 60 MB
     Arrays b = a; b.gate = gate2;
-    for (int window = 0; window < 3; ++window) {
+    for (int window = 0; window < 5; ++window) {
         cudaStreamAttrValue attr{};
-        if (window) {
+        if (window >= 3) {
+            int max_window = 0;
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, 0);
+            const size_t hotb = window == 3 ? npad * 8 : npad * 12, want = window == 3 ? npad * 8 : npad * 10;
+            CK(cudaCtxResetPersistingL2Cache());
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            attr.accessPolicyWindow.base_ptr = hot2;
+            attr.accessPolicyWindow.num_bytes = hotb < (size_t)max_window ? hotb : (size_t)max_window;
+            attr.accessPolicyWindow.hitRatio = window == 3 ? 1.0f : 0.83f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            printf("-- [fire32 | vis32 | gate]: %s\n", window == 3 ? "window over fire32 + vis32 only (40 MB set aside)" : "window over all three, 50 MB set aside, hit ratio 0.83");
+        } else if (window) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, 0);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, 0);
