@@ -23,7 +23,7 @@ EXEC_SERIAL, EXEC_EXACT, EXEC_PARALLEL = 0, 1, 2
 SRC_LIVE, SRC_SNAPSHOT = 0, 1
 RBAR_PASS_STEP, RBAR_METAL_TID0 = 0, 1
 GRAPH_REFERENCE, GRAPH_ER_BETA = 0, 1
-TABLE_AS_GIVEN, TABLE_DST_SORTED = 0, 1
+TABLE_AS_GIVEN, TABLE_DST_SORTED, TABLE_DST_INTERLEAVED = 0, 1, 2
 PROFILE_METAL_PARITY, PROFILE_NORTH_STAR, PROFILE_B200 = 0, 1, 2
 
 

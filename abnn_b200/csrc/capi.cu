@@ -105,9 +105,10 @@ struct abnn_handle {
     // abnn_engine_step: stimulus frame [in | expected | pTick | rate] and the captured pass
     float* d_frame = nullptr; float* h_frame = nullptr; cudaEvent_t frame_ev[RING]{}; int frame_pos = 0;
     cudaGraphExec_t step_exec = nullptr;
-    u64 step_events = 0; std::vector<u64> step_counts; bool step_pre[2]{}, step_post[2]{};
+    u64 step_events = 0; std::vector<u64> step_counts; bool step_pre[3]{}, step_post[3]{};
     u64 step_calls = 0, step_replays = 0;
     bool slack_ready = false;             // d.slack already holds the next pass's gate words (all but the in/out head)
+    bool fire_ready = false;              // d.fire32 / d.vis32 of the owned neurons are prepared for the next pass (all but the head)
     bool view_stale = false;              // remote slices of d.view were not refreshed by the last exchange
 };
 
@@ -315,6 +316,7 @@ int exchange_timestamps(abnn_handle* h, const KParams& kp)
     static const bool full = tune_env("ABNN_FULL_EXCHANGE") != nullptr;       // measurements only
     const u64 head = (u64)h->p.n_input + h->p.n_output;
     h->slack_ready = false;
+    h->fire_ready = kp.use_line32 != 0;                      // k_fold_prepare32 has written the owned neurons' words of the next pass
     if (h->p.world_size > 1) {
         if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
         if (slack_mode(h, kp) && h->slice >= head && !full && h->p2p) {
@@ -323,7 +325,7 @@ int exchange_timestamps(abnn_handle* h, const KParams& kp)
             h->slack_ready = true;
             h->view_stale = true;
         } else if (slack_mode(h, kp) && h->slice >= head && !full) {
-            CU(launch_build_slack(kp, h->d, h->d.live, h->lo, h->hi, h->st));
+            if (!kp.use_line32) CU(launch_build_slack(kp, h->d, h->d.live, h->lo, h->hi, h->st));   // else k_fold_prepare32 built the slice
             NC(ncclGroupStart());
             NC(ncclAllGather(h->d.slack + h->lo, h->d.slack, h->slice, ncclUint32, h->comm, h->st));
             NC(ncclBroadcast(h->d.live, h->d.view, head, ncclUint64, 0, h->comm, h->st));
@@ -334,7 +336,9 @@ int exchange_timestamps(abnn_handle* h, const KParams& kp)
             NC(ncclAllGather(h->d.live + h->lo, h->d.view, h->slice, ncclUint64, h->comm, h->st));
             h->view_stale = false;
         }
-    } else if (h->d.view != h->d.live && !kp.use_line32) {      // k_fold32 has already carried the pass's fires into the snapshot
+    } else if (kp.use_line32) {
+        h->slack_ready = true;                               // k_fold_prepare32: snapshot carried forward, every gate word rebuilt
+    } else if (h->d.view != h->d.live) {
         CU(cudaMemcpyAsync(h->d.view, h->d.live, h->N * sizeof(u64), cudaMemcpyDeviceToDevice, h->st));
     }
     return 0;
@@ -376,17 +380,23 @@ int append_chunk(abnn_handle* h, const abnn_synapse* host, u64 n)
 // Scratch (a second table + two key arrays) is allocated for the duration of the sort only.
 int sort_table(abnn_handle* h)
 {
-    if (h->p.table_order != ABNN_TABLE_DST_SORTED || h->n_local < 2) return 0;
+    if (h->p.table_order == ABNN_TABLE_AS_GIVEN || h->n_local < 2) return 0;
     const u64 n = h->n_local;
-    abnn_synapse* alt = nullptr; u32* keys = nullptr; void* tmp = nullptr;
+    const bool interleave = h->p.table_order == ABNN_TABLE_DST_INTERLEAVED;
+    abnn_synapse* alt = nullptr; u32* keys = nullptr; void* tmp = nullptr; u64* starts = nullptr;
     const size_t tmp_bytes = sort_by_dst_temp_bytes(n);
-    auto release = [&] { cudaFree(alt); cudaFree(keys); cudaFree(tmp); };
+    auto release = [&] { cudaFree(alt); cudaFree(keys); cudaFree(tmp); cudaFree(starts); };
     cudaError_t e = cudaMalloc(&alt, n * sizeof(abnn_synapse));
     if (e == cudaSuccess) e = cudaMalloc(&keys, 2 * n * sizeof(u32));
     if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess && interleave) e = cudaMalloc(&starts, (h->hi - h->lo + 1) * sizeof(u64));
     bool in_alt = false;
     int nb = 1; while ((1ull << nb) < h->N) ++nb;
     if (e == cudaSuccess) e = launch_sort_by_dst(h->d_syn, alt, keys, keys + n, n, nb, tmp, tmp_bytes, &in_alt, h->st);
+    if (e == cudaSuccess && interleave) {                    // sorted table -> interleaved, into the other buffer
+        e = launch_interleave_by_dst(in_alt ? alt : h->d_syn, in_alt ? h->d_syn : alt, n, (u32)h->lo, (u32)(h->hi - h->lo), starts, h->st);
+        in_alt = !in_alt;
+    }
     if (e == cudaSuccess && in_alt) e = cudaMemcpyAsync(h->d_syn, alt, n * sizeof(abnn_synapse), cudaMemcpyDeviceToDevice, h->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     release();
@@ -525,7 +535,7 @@ int abnn_default_params(abnn_params* p, uint32_t profile)
     p->filter_tau = 0.02; p->dt_sec = 0.0009; p->loss0 = 0.25;
     p->device = -1; p->rank = 0; p->world_size = 1; p->l2_persist = 1;
     p->sample_block = 1;
-    if (profile == ABNN_PROFILE_B200) { p->sample_block = 8; p->table_order = ABNN_TABLE_DST_SORTED; }
+    if (profile == ABNN_PROFILE_B200) { p->sample_block = 8; p->table_order = ABNN_TABLE_DST_INTERLEAVED; }
     return 0;
 }
 
@@ -561,7 +571,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (!p.world_size || p.rank >= p.world_size) return fail(ABNN_ERR_INVALID, "bad rank/world_size");
     if (p.sampler > 1 || p.release_rng > 1 || p.clock_mode > 1 || p.exec_mode > 2 || p.src_view > 1 || p.rbar_mode > 1)
         return fail(ABNN_ERR_INVALID, "unknown mode value");
-    if (p.table_order > ABNN_TABLE_DST_SORTED) return fail(ABNN_ERR_INVALID, "unknown table_order");
+    if (p.table_order > ABNN_TABLE_DST_INTERLEAVED) return fail(ABNN_ERR_INVALID, "unknown table_order");
     if (p.sample_block > 32 || (p.sample_block & (p.sample_block - 1)))
         return fail(ABNN_ERR_INVALID, "sample_block must be a power of two <= 32 (0 = 1)");
     if (!p.n_output || p.fir_size == 0 || p.fir_size > ABNN_MAX_FIR) return fail(ABNN_ERR_INVALID, "bad n_output / fir_size");
@@ -1018,7 +1028,7 @@ int abnn_load_state(abnn_handle* h, const char* path)
     if (cudaMemcpyAsync(h->d.sc, &sc, sizeof sc, cudaMemcpyHostToDevice, h->st) != cudaSuccess || cudaStreamSynchronize(h->st) != cudaSuccess)
         return fail(ABNN_ERR_CUDA, "device write failed during load");
     h->n_local = hd.n_local; h->n_local_all = counts; h->counts_dirty = false;
-    h->slack_ready = false; h->view_stale = false;
+    h->slack_ready = false; h->fire_ready = false; h->view_stale = false;
     return 0;
 }
 
@@ -1171,12 +1181,16 @@ static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t before_traverse,
     if (slack_mode(h, kp)) {
         kp.use_slack = 1;
         kp.use_line32 = line32_mode(h, kp) ? 1u : 0u;
-        u64 s0 = 0, s1 = h->N;          // gate words to (re)build from the snapshot
-        if (h->slack_ready) {           // the exchange delivered the gate words; inject / teacher forcing touched the head since
-            s1 = head_refreshed ? 0 : (u64)h->p.n_input + h->p.n_output;
+        const u64 head = (u64)h->p.n_input + h->p.n_output;
+        u64 s1 = h->N;                  // gate words [0, s1) to (re)build from the snapshot
+        if (h->slack_ready) {           // the last pass left the gate words; inject / teacher forcing touched the head since
+            s1 = head_refreshed ? 0 : head;
         } else RET(ensure_view(h));
-        if (kp.use_line32) CU(launch_prepare32(kp, h->d, h->d.view, s0, s1, h->lo, h->hi, h->st));   // + fire32 / vis32 of the owned neurons
-        else CU(launch_build_slack(kp, h->d, h->d.view, s0, s1, h->st));
+        if (kp.use_line32) {            // + fire32 / vis32 of the owned neurons: all of them, or the head after inject / teacher forcing
+            u64 o0 = h->lo, o1 = h->hi;
+            if (h->fire_ready) o1 = head_refreshed ? o0 : std::min(h->hi, std::max(h->lo, head));
+            CU(launch_prepare32(kp, h->d, h->d.view, 0, s1, o0, o1, h->st));
+        } else CU(launch_build_slack(kp, h->d, h->d.view, 0, s1, h->st));
     } else RET(ensure_view(h));
     if (before_traverse) CU(cudaEventRecord(before_traverse, h->st));
     switch (h->p.exec_mode) {
@@ -1186,7 +1200,7 @@ static int enqueue_pass(abnn_handle* h, KParams kp, cudaEvent_t before_traverse,
     }
     if (after_traverse) CU(cudaEventRecord(after_traverse, h->st));
     CU(launch_end_pass(kp, h->d.sc, h->d_stats, h->st));
-    if (kp.use_line32) CU(launch_fold32(h->d, h->lo, h->hi, h->st));   // the pass's fires / visits back into the 64-bit arrays
+    if (kp.use_line32) CU(launch_fold_prepare32(kp, h->d, h->lo, h->hi, h->st));   // fires / visits back into the 64-bit arrays + next pass's words
     RET(exchange_timestamps(h, kp));
     return 0;
 }
@@ -1227,7 +1241,9 @@ static int enqueue_step(abnn_handle* h, const KParams& kp)
 {
     const u32 ni = h->p.n_input, no = h->p.n_output;
     const bool refresh = slack_mode(h, kp) && h->slack_ready;
-    CU(launch_step_prologue(kp, h->d, h->d_frame, ni, no, h->p.teacher_gap, refresh, h->st));
+    const bool refresh_fire = refresh && h->fire_ready && line32_mode(h, kp);
+    // the head's words are brought up to date by the prologue only if BOTH word sets are ready (else enqueue_pass rebuilds)
+    CU(launch_step_prologue(kp, h->d, h->d_frame, ni, no, h->p.teacher_gap, refresh, refresh_fire, h->st));
     RET(enqueue_pass(h, kp, nullptr, nullptr, refresh));
     CU(launch_readout(kp, h->d, readout_params(h), h->rs, h->d_frame + ni, h->st));
     return 0;
@@ -1263,16 +1279,16 @@ int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, flo
     // With the peer-memory exchange (p2p_setup) the sharded sequence holds no NCCL call once the gate words are being
     // exchanged (slack_ready), so it can be captured too: opt-in on top of ABNN_P2P_EXCHANGE, not measured yet.
     static const bool p2p_graph = tune_env("ABNN_P2P_GRAPH") != nullptr;
-    const bool pre[2] = {h->slack_ready, h->view_stale};
+    const bool pre[3] = {h->slack_ready, h->view_stale, h->fire_ready};
     const bool sharded_ok = p2p_graph && h->p2p && pre[0] && slack_mode(h, kp) && h->slice >= (u64)h->p.n_input + h->p.n_output &&
                             !tune_env("ABNN_FULL_EXCHANGE");
     const bool capturable = h->p.exec_mode == ABNN_EXEC_PARALLEL && (h->p.world_size == 1 || sharded_ok) && !no_graph;
     const bool match = h->step_exec && h->step_events == events && h->step_counts == h->n_local_all &&
-                       h->step_pre[0] == pre[0] && h->step_pre[1] == pre[1];
+                       h->step_pre[0] == pre[0] && h->step_pre[1] == pre[1] && h->step_pre[2] == pre[2];
     ++h->step_calls;
     if (capturable && match) {
         CU(cudaGraphLaunch(h->step_exec, h->st));
-        h->slack_ready = h->step_post[0]; h->view_stale = h->step_post[1];
+        h->slack_ready = h->step_post[0]; h->view_stale = h->step_post[1]; h->fire_ready = h->step_post[2];
         ++h->step_replays;
     } else if (capturable && h->step_calls > 1) {
         // second call onwards (the first one warms up lazily configured kernels): record this state's
@@ -1285,16 +1301,19 @@ int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, flo
         if (rc != 0 || e != cudaSuccess || !g) {
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
-            h->slack_ready = pre[0]; h->view_stale = pre[1];
+            h->slack_ready = pre[0]; h->view_stale = pre[1]; h->fire_ready = pre[2];
             if (rc != 0) return rc;
             return fail(ABNN_ERR_CUDA, std::string("engine_step: stream capture failed: ") + cudaGetErrorString(e));
         }
         const cudaError_t ei = cudaGraphInstantiate(&h->step_exec, g, 0);
         cudaGraphDestroy(g);
-        if (ei != cudaSuccess) { h->step_exec = nullptr; h->slack_ready = pre[0]; h->view_stale = pre[1]; return fail(ABNN_ERR_CUDA, "engine_step: cudaGraphInstantiate failed"); }
+        if (ei != cudaSuccess) {
+            h->step_exec = nullptr; h->slack_ready = pre[0]; h->view_stale = pre[1]; h->fire_ready = pre[2];
+            return fail(ABNN_ERR_CUDA, "engine_step: cudaGraphInstantiate failed");
+        }
         h->step_events = events; h->step_counts = h->n_local_all;
-        h->step_pre[0] = pre[0]; h->step_pre[1] = pre[1];
-        h->step_post[0] = h->slack_ready; h->step_post[1] = h->view_stale;
+        h->step_pre[0] = pre[0]; h->step_pre[1] = pre[1]; h->step_pre[2] = pre[2];
+        h->step_post[0] = h->slack_ready; h->step_post[1] = h->view_stale; h->step_post[2] = h->fire_ready;
         CU(cudaGraphLaunch(h->step_exec, h->st));
         ++h->step_replays;
     } else {
@@ -1486,6 +1505,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
             }
             s.pruned = h->n_local - kept;
             h->n_local = kept;
+            if (s.pruned && h->p.table_order == ABNN_TABLE_DST_INTERLEAVED) RET(sort_table(h));   // the interleaved order is re-derived after every change
         }
         // 2. grow: candidates in event order, as many as fit
         if (owned) {
@@ -1528,7 +1548,7 @@ int abnn_download_timestamps(abnn_handle* h, uint64_t* lf, uint64_t* lv)
 int abnn_upload_timestamps(abnn_handle* h, const uint64_t* lf, const uint64_t* lv)
 {
     RET(use(h));
-    h->slack_ready = false;
+    h->slack_ready = false; h->fire_ready = false;
     if (lf) h->view_stale = false;
     if (lf) {
         CU(cudaMemcpyAsync(h->d.live, lf, h->N * sizeof(u64), cudaMemcpyHostToDevice, h->st));
@@ -1559,7 +1579,7 @@ int abnn_get_clock(abnn_handle* h, uint64_t* clock)
 int abnn_set_clock(abnn_handle* h, uint64_t clock)
 {
     RET(use(h));
-    h->slack_ready = false;             // the gate words are relative to the clock
+    h->slack_ready = false; h->fire_ready = false;   // the gate and fire words are relative to the clock
     k_set_clock<<<1, 1, 0, h->st>>>(h->d.sc, clock);
     CU(cudaGetLastError());
     return 0;

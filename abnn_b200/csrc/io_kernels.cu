@@ -45,7 +45,7 @@ __global__ void k_teacher(const __grid_constant__ KParams kp, const DevPtrs d, c
 // (frame = [in | expected | pTick | rate] in device memory), and — when the exchange already delivered the
 // gate words of this pass — the refresh of the head's words, which these two steps may just have changed.
 __global__ void k_step_prologue(const __grid_constant__ KParams kp, const DevPtrs d, const float* __restrict__ frame,
-                                u32 n_in, u32 n_out, u64 gap, u32 refresh_slack)
+                                u32 n_in, u32 n_out, u64 gap, u32 refresh_slack, u32 refresh_fire)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_in + n_out) return;
@@ -67,6 +67,8 @@ __global__ void k_step_prologue(const __grid_constant__ KParams kp, const DevPtr
         if (i >= kp.neuron_lo && i < kp.neuron_hi) d.live[i] = now;
     }
     if (refresh_slack) d.slack[i] = slack_word(now, lp, kp.window_pre);
+    // k_traverse_line32's fire word of an owned head neuron (traversal.cu:k_fold_prepare32 wrote it before this step's spikes)
+    if (refresh_fire && i >= kp.neuron_lo && i < kp.neuron_hi) d.fire32[i] = fire_word(now, d.live[i]);
 }
 
 // Brain::read_outputs (brain.cpp:145-157), window = ticks of the last pass.
@@ -157,10 +159,11 @@ cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* exp
     return cudaGetLastError();
 }
 cudaError_t launch_step_prologue(const KParams& kp, const DevPtrs& d, const float* frame, u32 n_in, u32 n_out, u64 gap,
-                                 bool refresh_slack, cudaStream_t st)
+                                 bool refresh_slack, bool refresh_fire, cudaStream_t st)
 {
     if (!(n_in + n_out)) return cudaSuccess;
-    k_step_prologue<<<(n_in + n_out + 255) / 256, 256, 0, st>>>(kp, d, frame, n_in, n_out, gap, refresh_slack ? 1u : 0u);
+    k_step_prologue<<<(n_in + n_out + 255) / 256, 256, 0, st>>>(kp, d, frame, n_in, n_out, gap, refresh_slack ? 1u : 0u,
+                                                                refresh_fire ? 1u : 0u);
     return cudaGetLastError();
 }
 cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st)

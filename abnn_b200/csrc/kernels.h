@@ -14,8 +14,9 @@ bool line_kernel_selected(const KParams& kp);
 bool line32_selected(const KParams& kp);
 // gate words of [s0,s1) from the snapshot `src`, fire32 / vis32 of the owned neurons [o0,o1) from the 64-bit lastFired
 cudaError_t launch_prepare32(const KParams& kp, const DevPtrs& d, const u64* src, u64 s0, u64 s1, u64 o0, u64 o1, cudaStream_t st);
-// fires and visits of the pass back into lastFired / snapshot / lastVisited of [o0,o1); runs after k_end_pass
-cudaError_t launch_fold32(const DevPtrs& d, u64 o0, u64 o1, cudaStream_t st);
+// after k_end_pass: fires and visits of the pass back into lastFired / snapshot / lastVisited of the owned neurons [o0,o1),
+// and their gate / fire / visit words for the next pass
+cudaError_t launch_fold_prepare32(const KParams& kp, const DevPtrs& d, u64 o0, u64 o1, cudaStream_t st);
 cudaError_t launch_end_pass(const KParams& kp, DevScalars* sc, abnn_pass_stats* out, cudaStream_t st);
 
 // exchange.cu — the per-pass exchange of a sharded PARALLEL run as peer-memory stores (opt-in, see capi.cu:p2p_setup)
@@ -53,7 +54,7 @@ cudaError_t launch_teacher(const KParams& kp, const DevPtrs& d, const float* exp
                            cudaStream_t st);
 // inject + teacher forcing (+ gate-word refresh of the head) in one launch; frame = [in | expected | pTick | rate]
 cudaError_t launch_step_prologue(const KParams& kp, const DevPtrs& d, const float* frame, u32 n_in, u32 n_out, u64 gap,
-                                 bool refresh_slack, cudaStream_t st);
+                                 bool refresh_slack, bool refresh_fire, cudaStream_t st);
 cudaError_t launch_read_outputs(const KParams& kp, const DevPtrs& d, unsigned char* spikes, u32 n_out, cudaStream_t st);
 cudaError_t launch_readout(const KParams& kp, const DevPtrs& d, const ReadoutParams& rp, const ReadoutState& rs,
                            const float* expected, cudaStream_t st);
@@ -91,6 +92,10 @@ cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 
 size_t sort_by_dst_temp_bytes(u64 n);
 cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, u32* keys_alt, u64 n, int key_bits,
                                void* tmp, size_t tmp_bytes, bool* result_in_alt, cudaStream_t st);
+
+// ABNN_TABLE_DST_INTERLEAVED: the dst-sorted table `in` (n records, destinations in [lo, lo + span)) interleaved per group of
+// 8 neurons into `out` (must not alias); start: span + 1 u64 of scratch (run starts).
+cudaError_t launch_interleave_by_dst(const abnn_synapse* in, abnn_synapse* out, u64 n, u32 lo, u32 span, u64* start, cudaStream_t st);
 
 // Stable insertion of m new records (sorted by dst, ties in append order) into the dst-sorted table of n records,
 // out of place: out[0 .. n+m). cnt: dst_span + 1 zeroed u32 slots (per-neuron histogram -> prefix sums).

@@ -34,14 +34,17 @@ __device__ __forceinline__ bool release_test(const KParams& kp, float w, float u
     const float p = clampf(w * w * kp.base_scale, 0.f, 1.f);     // brain.metal:91
     return p > u;                                                // brain.metal:92
 }
-__device__ __forceinline__ float plasticity(const KParams& kp, float w, bool fired, float R, float rbar, u64 isi_ticks)
+__device__ __forceinline__ float plasticity_f(const KParams& kp, float w, bool fired, float R, float rbar, float isi)
 {
     float dW = fired ? (kp.a_ltp * (1.f - w)) : (-kp.a_ltd * w);              // brain.metal:101-102
     dW += kp.eta_reward * (R - rbar) * (fired ? 1.0f : 0.0f);                 // brain.metal:107
-    const float isi = (float)isi_ticks;                                       // brain.metal:116 (now - ld)
     const float est = isi > 0.f ? kp.home_tick_hz / isi : 0.f;                // brain.metal:117
     dW += kp.eta_home * (kp.target_rate_hz - est) * w;                        // brain.metal:118
     return clampf(w + dW, kp.w_min, kp.w_max);                                // brain.metal:121
+}
+__device__ __forceinline__ float plasticity(const KParams& kp, float w, bool fired, float R, float rbar, u64 isi_ticks)
+{
+    return plasticity_f(kp, w, fired, R, rbar, (float)isi_ticks);             // brain.metal:116 (now - ld)
 }
 __device__ __forceinline__ u64 event_now(const KParams& kp, u64 clock, u64 i)
 {
@@ -829,7 +832,11 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 const int gap = (int)t - fire[j];                                           // |gap| < 2^31
                 const bool open = ((candm >> k) & 1u) && (u32)(gap < 0 ? -gap : gap) > refr;   // brain.metal:79-83
                 const unsigned cm = __ballot_sync(0xffffffffu, open);
-                if (open) queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
+                if (open) {
+                    queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
+                    // the fire word travels to the dense step in the record's unused pad slot of the stage
+                    *reinterpret_cast<int*>(const_cast<unsigned char*>(mine) + k * 512 + 12) = fire[j];
+                }
                 nC += __popc(cm);
             }
         }
@@ -839,22 +846,20 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         // ---- C: dense steps over the queue ----------------------------------------------------------------
         u32 nf = 0;                                          // destinations that fired in this chunk so far (warp-uniform)
         bool spilled = false;
-        u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0); int fv = 0;
+        u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0);            // sy.w = fire32[dst] as read in phase A
         bool cand = lane < nC;
         if (cand) {
             le = queue[lane];
             sy = *reinterpret_cast<const uint4*>(stage + le * 16);                          // brain.metal:70
-            fv = __ldcg(d.fire32 + sy.y);                                                   // brain.metal:79
         }
         u32 j = 0;
 #pragma unroll 1
         while (j < nC) {
-            u32 le_n = 0; uint4 sy_n = make_uint4(0, 0, 0, 0); int fv_n = 0;
+            u32 le_n = 0; uint4 sy_n = make_uint4(0, 0, 0, 0);
             const bool cand_n = j + 32 + lane < nC;
-            if (cand_n) {                                    // next step's record and fire32[dst] on their way
+            if (cand_n) {                                    // next step's record
                 le_n = queue[j + 32 + lane];
                 sy_n = *reinterpret_cast<const uint4*>(stage + le_n * 16);
-                fv_n = __ldcg(d.fire32 + sy_n.y);
             }
             const u32 g = le >> LOGB, r8 = le & 7u;
             const u64 edge = (__shfl_sync(0xffffffffu, m, g) & ~7ull) + r8;
@@ -874,10 +879,10 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             }
             float w = __uint_as_float(sy.z);
             bool skip = true, want = false;
-            int gap = 0;
+            int gap = 0, fv = (int)sy.w;
             if (cand) {
                 if ((dupm >> g) & 1u) w = __ldcg(&d.syn[edge].w);
-                if (spilled) fv = __ldcg(d.fire32 + sy.y);
+                if (spilled) fv = __ldcg(d.fire32 + sy.y);                                  // brain.metal:79
                 gap = (int)t - fv;
                 skip = (u32)(gap < 0 ? -gap : gap) <= refr;                                 // brain.metal:79-83
                 if (!spilled)
@@ -897,12 +902,12 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 gated = !skip && (int)lane <= first;
             }
             if (gated) {
-                u64 isi = (u64)(u32)(gap < 0 ? -gap : gap);
+                float isi = (float)(u32)(gap < 0 ? -gap : gap);                             // brain.metal:116 (now - ld)
                 if (fv == FIRE32_ANCIENT || fv == FIRE32_FUTURE) {   // beyond 2^30 ticks: the exact inter-spike interval
                     const u64 ld = __ldcg(d.live + sy.y), now = clock + t;
-                    isi = ld <= now ? now - ld : ld - now;
+                    isi = (float)(ld <= now ? now - ld : ld - now);
                 }
-                __stcg(&d.syn[edge].w, plasticity(kp, w, fired, R, rbar, isi));             // brain.metal:101-122
+                __stcg(&d.syn[edge].w, plasticity_f(kp, w, fired, R, rbar, isi));           // brain.metal:101-122
             }
             if (fired) {
                 atomicMax(d.fire32 + sy.y, (int)t);                                         // brain.metal:125-126
@@ -919,13 +924,12 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             }
             if (dupm | (u32)spilled) __threadfence();        // rare: make this step's writes visible to the re-reads
             j += adv;
-            if (adv == 32) { cand = cand_n; le = le_n; sy = sy_n; fv = fv_n; }
+            if (adv == 32) { cand = cand_n; le = le_n; sy = sy_n; }
             else {                                           // a cut step: take up again behind it
                 cand = j + lane < nC;
                 if (cand) {
                     le = queue[j + lane];
                     sy = *reinterpret_cast<const uint4*>(stage + le * 16);
-                    fv = __ldcg(d.fire32 + sy.y);
                 }
             }
         }
@@ -945,17 +949,28 @@ __global__ void __launch_bounds__(256) k_prepare32(const __grid_constant__ KPara
     for (u64 n = s0 + tid; n < s1; n += step) d.slack[n] = slack_word(clock, src[n], kp.window_pre);
     for (u64 n = o0 + tid; n < o1; n += step) { d.fire32[n] = fire_word(clock, d.live[n]); d.vis32[n] = 0u; }
 }
-// After the pass (k_end_pass has advanced the clock): fires and visits of the pass back into the 64-bit arrays. A
-// non-negative fire32 is lastFired - pass start (a fire of this pass, or an uploaded future timestamp that no fire
-// overtook — the same value it already has); the snapshot entry follows (single GPU: snapshot == lastFired between passes).
-__global__ void __launch_bounds__(256) k_fold32(const DevPtrs d, u64 o0, u64 o1)
+// After the pass (k_end_pass has advanced the clock), one sweep over the owned neurons [o0, o1): the pass's fires and
+// visits go back into the 64-bit arrays, and the three 32-bit words of the NEXT pass are written in the same breath
+// (gate word as k_build_slack would build it from the new lastFired, fire word relative to the new clock, visit word
+// cleared) — so a steady run never reads the 64-bit arrays at the start of a pass.
+// A non-negative fire32 is lastFired - pass start: a fire of this pass, or an uploaded future timestamp that no fire
+// overtook (the value the 64-bit array already holds). Single GPU: snapshot == lastFired between passes, kept here.
+__global__ void __launch_bounds__(256) k_fold_prepare32(const __grid_constant__ KParams kp, const DevPtrs d, u64 o0, u64 o1)
 {
-    const u64 start = d.sc->clock - d.sc->last_pass_ticks;
+    const u64 clock = d.sc->clock, start = clock - d.sc->last_pass_ticks;
     for (u64 n = o0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; n < o1; n += (u64)gridDim.x * blockDim.x) {
         const int f = d.fire32[n];
-        if (f >= 0 && f != FIRE32_FUTURE) { d.live[n] = start + (u32)f; d.view[n] = start + (u32)f; }
         const u32 v = d.vis32[n];
-        if (v) { const u64 tv = start + v - 1u; if (d.visited[n] < tv) d.visited[n] = tv; }
+        u64 lf;
+        if (f == FIRE32_ANCIENT || f == FIRE32_FUTURE) lf = d.live[n];            // beyond 2^30 ticks: the 64-bit value is the truth
+        else {
+            lf = start + (u64)(long long)f;
+            if (f >= 0) { d.live[n] = lf; d.view[n] = lf; }                          // brain.metal:125-126, folded
+        }
+        if (v) { const u64 tv = start + v - 1u; if (d.visited[n] < tv) d.visited[n] = tv; }   // README.md:84, folded
+        d.slack[n] = slack_word(clock, lf, kp.window_pre);
+        d.fire32[n] = fire_word(clock, lf);
+        d.vis32[n] = 0u;
     }
 }
 cudaError_t launch_prepare32(const KParams& kp, const DevPtrs& d, const u64* src, u64 s0, u64 s1, u64 o0, u64 o1, cudaStream_t st)
@@ -969,12 +984,12 @@ cudaError_t launch_prepare32(const KParams& kp, const DevPtrs& d, const u64* src
     k_prepare32<<<(unsigned)blocks, 256, 0, st>>>(kp, d, src, s0, s1, o0, o1);
     return cudaGetLastError();
 }
-cudaError_t launch_fold32(const DevPtrs& d, u64 o0, u64 o1, cudaStream_t st)
+cudaError_t launch_fold_prepare32(const KParams& kp, const DevPtrs& d, u64 o0, u64 o1, cudaStream_t st)
 {
     if (o1 <= o0) return cudaSuccess;
     u64 blocks = (o1 - o0 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_fold32<<<(unsigned)blocks, 256, 0, st>>>(d, o0, o1);
+    k_fold_prepare32<<<(unsigned)blocks, 256, 0, st>>>(kp, d, o0, o1);
     return cudaGetLastError();
 }
 

@@ -81,17 +81,26 @@ enum abnn_graph_kind {
 };
 enum abnn_table_order {     /* HBM layout of this rank's synapse table                       */
     ABNN_TABLE_AS_GIVEN   = 0,/*  records stay in upload / generation order (brain-engine.cpp:37-52)  */
-    ABNN_TABLE_DST_SORTED = 1 /*  stable sort by dst after every upload / init / load / growth step: the
+    ABNN_TABLE_DST_SORTED = 1,/*  stable sort by dst after every upload / init / load / growth step: the
                                  records that target one neuron are contiguous, so a 128-byte line of
                                  the table (sample_block = 8) touches one lastFired/lastVisited sector
                                  instead of eight. Table order is part of the semantics (edge(e) indexes
                                  it); the oracle applies the same stable sort.                  */
+    ABNN_TABLE_DST_INTERLEAVED = 2 /* DST_SORTED with the records of every group of 8 consecutive neurons (id >> 3)
+                                 interleaved: inside a group the order is (rank of the record among its
+                                 destination's records, destination), i.e. row r of a group holds the r-th record
+                                 of each of its neurons. A 128-byte line still touches ONE sector of the per-neuron
+                                 arrays (8 adjacent neurons), but no two events of a sample group hit the same
+                                 neuron: every neuron sees the event arrival statistics of the iid sampler (with
+                                 DST_SORTED its events arrive in bursts of sample_block, which lowers the fire rate
+                                 by a few per cent — DESIGN.md §2). Re-derived after every upload / init / load
+                                 and after every structural step that changed the table.        */
 };
 enum abnn_profile {
     ABNN_PROFILE_METAL_PARITY = 0, /* SWEEP, XORSHIFT, PER_PASS, SERIAL, LIVE, METAL_TID0, budget 2560 */
     ABNN_PROFILE_NORTH_STAR   = 1, /* PHILOX, PHILOX, PER_EVENT, PARALLEL, SNAPSHOT, PASS_STEP          */
     ABNN_PROFILE_B200         = 2  /* NORTH_STAR with the layout the B200 kernel is built for: sample_block 8
-                                      (one 128-byte line per draw) over a DST_SORTED table — what bench.py times */
+                                      (one 128-byte line per draw) over a DST_INTERLEAVED table — what bench.py times */
 };
 
 /* ---- L3: every compile-time knob of the reference as a runtime parameter ------------------

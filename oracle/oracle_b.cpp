@@ -106,15 +106,37 @@ void recount(ob_handle* h)
 // ABNN_TABLE_DST_SORTED (include/abnn.h): stable sort of the shard's table by dst (counting sort:
 // records with equal dst keep their relative order). No reference counterpart — a layout rule of
 // the north-star design; table order matters because edge(e) indexes the table.
+//
+// ABNN_TABLE_DST_INTERLEAVED: the dst-sorted table with the records of every group of 8 consecutive neurons
+// (global id >> 3) interleaved — inside a group the order is (rank of the record among its destination's records,
+// destination): row r of the group holds the r-th record of each of its neurons that has one. A 128-byte line then
+// holds records of 8 adjacent destinations, so no two events of a sample group hit the same neuron.
 void sort_table(ob_handle* h)
 {
-    if (h->p.table_order != ABNN_TABLE_DST_SORTED || h->syn.empty()) return;
+    if (h->p.table_order == ABNN_TABLE_AS_GIVEN || h->syn.empty()) return;
     const uint64_t span = h->hi - h->lo;
     std::vector<uint64_t> start(span + 1, 0);
     for (const auto& s : h->syn) ++start[s.dst - h->lo + 1];
     for (uint64_t d = 0; d < span; ++d) start[d + 1] += start[d];
+    std::vector<uint64_t> first(start);                    // start of every destination's run (start[] is advanced below)
     std::vector<abnn_synapse> out(h->syn.size());
     for (const auto& s : h->syn) out[start[s.dst - h->lo]++] = s;
+    h->syn.swap(out);
+    if (h->p.table_order != ABNN_TABLE_DST_INTERLEAVED) return;
+    uint64_t o = 0;
+    for (uint64_t g0 = h->lo & ~7ull; g0 < h->hi; g0 += 8) {      // groups are aligned on the GLOBAL neuron id
+        uint64_t cnt[8], beg[8], rows = 0;
+        for (uint64_t k = 0; k < 8; ++k) {
+            const uint64_t nid = g0 + k;
+            const bool mine = nid >= h->lo && nid < h->hi;
+            beg[k] = mine ? first[nid - h->lo] : 0;
+            cnt[k] = mine ? first[nid - h->lo + 1] - first[nid - h->lo] : 0;
+            rows = std::max(rows, cnt[k]);
+        }
+        for (uint64_t r = 0; r < rows; ++r)
+            for (uint64_t k = 0; k < 8; ++k)
+                if (r < cnt[k]) out[o++] = h->syn[beg[k] + r];
+    }
     h->syn.swap(out);
 }
 }  // namespace
@@ -484,6 +506,7 @@ uint64_t ob_prune(ob_handle* h)
     size_t o = 0;
     for (size_t i = 0; i < n0; ++i) if (!(h->syn[i].w < wp)) h->syn[o++] = h->syn[i];
     h->syn.resize(o);
+    if (o != n0 && h->p.table_order == ABNN_TABLE_DST_INTERLEAVED) sort_table(h);   // the interleaved order is re-derived after every change
     return n0 - o;
 }
 // Staged growth candidates of this shard: (order, src, dst) triples, 16 bytes each.

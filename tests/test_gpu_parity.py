@@ -233,6 +233,38 @@ def test_dst_sorted_table_bit_exact(mode):
     assert_same_state(b, o)
 
 
+@pytest.mark.parametrize("mode", [capi.EXEC_SERIAL, capi.EXEC_EXACT])
+def test_dst_interleaved_table_bit_exact(mode):
+    """ABNN_TABLE_DST_INTERLEAVED: the device's radix sort + per-group interleave == the oracle's, after upload and after a
+    structural step that prunes and grows (the order is re-derived on both sides); SERIAL and EXACT stay bit-exact."""
+    rng = np.random.default_rng(22)
+    N, n = 5000, 300_007
+    syn = random_graph(rng, n, N, 0.2, 1.0, dst_lo=16)
+    pre = rng.integers(1, 40_000, N).astype(np.uint64)
+    over = dict(n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, exec_mode=mode, sample_block=8,
+                table_order=capi.TABLE_DST_INTERLEAVED, window_pre=250_000, refractory=30_000, p_new=0.1, w_prune=0.21,
+                syn_capacity=n + 20_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(pre, None); x.clock = 40_000; x.set_reward(0.1)
+    got = b.download_synapses()
+    assert got.tobytes() == o.download_synapses().tobytes()
+    s = syn[np.argsort(syn["dst"], kind="stable")]                      # independent restatement of the order in numpy
+    first = np.searchsorted(s["dst"], s["dst"], side="left")
+    rank = np.arange(n) - first
+    assert got.tobytes() == s[np.lexsort((s["dst"] & 7, rank, s["dst"] >> 3))].tobytes()
+    for p in range(3):
+        sb, so = b.run_pass(100_001), o.run_pass(100_001)
+        assert_same_stats(sb, so, f"pass {p}")
+        assert so.gated > 500
+        if p == 1:
+            ssb, sso = b.prune_and_grow(), o.prune_and_grow()
+            assert (ssb.pruned, ssb.appended, ssb.n_after) == (sso.pruned, sso.appended, sso.n_after)
+            assert sso.appended > 0 and sso.pruned > 0
+            assert b.download_synapses().tobytes() == o.download_synapses().tobytes()
+    assert_same_state(b, o)
+
+
 def test_line_kernel_sorted_table_single_warp_chains_exact():
     """PARALLEL line kernel over a dst-sorted table with ONE chunk in flight per destination: 64 destinations
     with 4096 synapses each and passes of 256 events (= one warp, one chunk). Lines of a chunk share

@@ -103,6 +103,11 @@ template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arr
                 acc += __ldcg(a.fire32 + dst);
                 atomicMax(a.vis32 + dst, (u32)(c * 256 + k * 32 + lane));
             }
+            if (LEVEL == 8) {                                                                 // interleaved order: the 8 records of a line
+                const u32 dst = ((u32)__umul64hi(mix(line), a.n_neuron - 8) & ~7u) + rec;     // target 8 ADJACENT neurons (one sector)
+                acc += __ldcg(a.fire32 + dst);
+                atomicMax(a.vis32 + dst, (u32)(c * 256 + k * 32 + lane));
+            }
             if (LEVEL == 7 && rec == 7) {                                                     // packed, read only (no RED)
                 const u32 dst = (u32)__umul64hi(mix(line), a.n_neuron);
                 acc += __ldcg(reinterpret_cast<const u32*>(a.dstw + dst) + 1);
@@ -166,6 +171,7 @@ int main(int argc, char** argv)
     CK(cudaFuncSetAttribute(k_line_staged<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
+    CK(cudaFuncSetAttribute(k_line_staged<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     auto report = [&](const char* name, float ms, double bytes_per_event) {
         printf("%-64s %.3f ms  %6.1f Gev/s  %5.2f TB/s algorithmic\n", name, ms, events / ms / 1e6, events * bytes_per_event / ms / 1e9);
     };
@@ -239,6 +245,7 @@ int main(int argc, char** argv)
         report("L7 + 4-byte read per line of packed dstw (40 MB)", timeit([&] { k_line_staged<7><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
         report("L5 + RED.MAX.32 on the same 8-byte word", timeit([&] { k_line_staged<5><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
         report("L6 fire32 / vis32 as two 20 MB arrays (read + RED.MAX.32)", timeit([&] { k_line_staged<6><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+        report("L8 same, 8 adjacent neurons per line (read + RED per record)", timeit([&] { k_line_staged<8><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
     }
     return 0;
 }
