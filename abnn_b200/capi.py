@@ -24,6 +24,7 @@ SRC_LIVE, SRC_SNAPSHOT = 0, 1
 RBAR_PASS_STEP, RBAR_METAL_TID0 = 0, 1
 GRAPH_REFERENCE, GRAPH_ER_BETA = 0, 1
 TABLE_AS_GIVEN, TABLE_DST_SORTED, TABLE_DST_INTERLEAVED = 0, 1, 2
+EXCHANGE_NCCL, EXCHANGE_PEER = 0, 1
 PROFILE_METAL_PARITY, PROFILE_NORTH_STAR, PROFILE_B200 = 0, 1, 2
 
 
@@ -53,7 +54,7 @@ class Params(C.Structure):
         ("filter_tau", C.c_double), ("dt_sec", C.c_double), ("loss0", C.c_double),
         ("device", C.c_int32), ("rank", C.c_uint32), ("world_size", C.c_uint32),
         ("l2_persist", C.c_uint32),
-        ("sample_block", C.c_uint32), ("table_order", C.c_uint32), ("reserved_", C.c_uint32 * 2),
+        ("sample_block", C.c_uint32), ("table_order", C.c_uint32), ("prune_in_place", C.c_uint32), ("exchange", C.c_uint32),
     ]
 
     def copy(self) -> "Params":

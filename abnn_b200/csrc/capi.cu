@@ -233,35 +233,42 @@ int p2p_setup(abnn_handle* h)
 {
     const u32 W = h->p.world_size, me = h->p.rank;
     if (W < 2 || W > P2P_MAX_WORLD || !h->d.slack) return 0;
-    CU(cudaMalloc(&h->d_p2p, P2P_WORDS * sizeof(u64)));
-    CU(cudaMemsetAsync(h->d_p2p, 0, P2P_WORDS * sizeof(u64), h->st));
     struct Pair { cudaIpcMemHandle_t ts, flags; };
     static_assert(sizeof(Pair) == 128, "two 64-byte IPC handles");
-    Pair mine{};
-    CU(cudaIpcGetMemHandle(&mine.ts, h->d_ts));
-    CU(cudaIpcGetMemHandle(&mine.flags, h->d_p2p));
-    Pair* d_all = nullptr;
-    CU(cudaMalloc(&d_all, (size_t)W * sizeof(Pair)));
-    CU(cudaMemcpyAsync(d_all + me, &mine, sizeof(Pair), cudaMemcpyHostToDevice, h->st));
-    NC(ncclAllGather(d_all + me, d_all, sizeof(Pair), ncclUint8, h->comm, h->st));
-    std::vector<Pair> all(W);
-    CU(cudaMemcpyAsync(all.data(), d_all, (size_t)W * sizeof(Pair), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    // A rank-local failure must not keep this rank out of the two collectives below (the peers would wait for it in NCCL
+    // forever): it only clears `ok`, which the all-reduce turns into "NCCL exchange on every rank".
     int ok = 1;
-    for (u32 r = 0; r < W && ok; ++r) {
-        if (r == me) { h->peer_ts[r] = h->d_ts; h->peer_flags[r] = h->d_p2p; continue; }
-        if (cudaIpcOpenMemHandle(&h->peer_ts[r], all[r].ts, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&h->peer_flags[r], all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            ok = 0;
+    Pair mine{};
+    Pair* d_all = nullptr;
+    if (cudaMalloc(&h->d_p2p, P2P_WORDS * sizeof(u64)) != cudaSuccess) { h->d_p2p = nullptr; ok = 0; }
+    if (ok && (cudaMemsetAsync(h->d_p2p, 0, P2P_WORDS * sizeof(u64), h->st) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.ts, h->d_ts) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, h->d_p2p) != cudaSuccess)) ok = 0;
+    cudaGetLastError();
+    CU(cudaMalloc(&d_all, (size_t)W * sizeof(Pair)));      // 1 KB: if even this fails the handle is unusable anyway
+    std::vector<Pair> all(W);
+    auto collectives = [&]() -> int {
+        CU(cudaMemcpyAsync(d_all + me, &mine, sizeof(Pair), cudaMemcpyHostToDevice, h->st));
+        NC(ncclAllGather(d_all + me, d_all, sizeof(Pair), ncclUint8, h->comm, h->st));
+        CU(cudaMemcpyAsync(all.data(), d_all, (size_t)W * sizeof(Pair), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        for (u32 r = 0; r < W && ok; ++r) {
+            if (r == me) { h->peer_ts[r] = h->d_ts; h->peer_flags[r] = h->d_p2p; continue; }
+            if (cudaIpcOpenMemHandle(&h->peer_ts[r], all[r].ts, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&h->peer_flags[r], all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            }
         }
-    }
-    int* d_ok = reinterpret_cast<int*>(d_all);
-    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->st));
-    NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->st));
-    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
-    CU(cudaFree(d_all));
+        int* d_ok = reinterpret_cast<int*>(d_all);
+        CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->st));
+        NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->st));
+        CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        return 0;
+    };
+    const int rc = collectives();
+    cudaFree(d_all);                                        // on every path
+    if (rc != 0) return rc;
     if (!ok) {                                               // NCCL exchange on every rank
         for (u32 r = 0; r < W; ++r) {
             if (r != me && h->peer_ts[r]) cudaIpcCloseMemHandle(h->peer_ts[r]);
@@ -394,7 +401,8 @@ int sort_table(abnn_handle* h)
     int nb = 1; while ((1ull << nb) < h->N) ++nb;
     if (e == cudaSuccess) e = launch_sort_by_dst(h->d_syn, alt, keys, keys + n, n, nb, tmp, tmp_bytes, &in_alt, h->st);
     if (e == cudaSuccess && interleave) {                    // sorted table -> interleaved, into the other buffer
-        e = launch_interleave_by_dst(in_alt ? alt : h->d_syn, in_alt ? h->d_syn : alt, n, (u32)h->lo, (u32)(h->hi - h->lo), starts, h->st);
+        e = launch_interleave_by_dst(in_alt ? alt : h->d_syn, in_alt ? h->d_syn : alt, n, (u32)h->lo, (u32)(h->hi - h->lo),
+                                     h->p.sample_block >= 16 ? 16u : 8u, starts, h->st);
         in_alt = !in_alt;
     }
     if (e == cudaSuccess && in_alt) e = cudaMemcpyAsync(h->d_syn, alt, n * sizeof(abnn_synapse), cudaMemcpyDeviceToDevice, h->st);
@@ -572,6 +580,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (p.sampler > 1 || p.release_rng > 1 || p.clock_mode > 1 || p.exec_mode > 2 || p.src_view > 1 || p.rbar_mode > 1)
         return fail(ABNN_ERR_INVALID, "unknown mode value");
     if (p.table_order > ABNN_TABLE_DST_INTERLEAVED) return fail(ABNN_ERR_INVALID, "unknown table_order");
+    if (p.exchange > ABNN_EXCHANGE_PEER || p.prune_in_place > 1) return fail(ABNN_ERR_INVALID, "unknown exchange / prune_in_place value");
     if (p.sample_block > 32 || (p.sample_block & (p.sample_block - 1)))
         return fail(ABNN_ERR_INVALID, "sample_block must be a power of two <= 32 (0 = 1)");
     if (!p.n_output || p.fir_size == 0 || p.fir_size > ABNN_MAX_FIR) return fail(ABNN_ERR_INVALID, "bad n_output / fir_size");
@@ -789,7 +798,7 @@ int abnn_comm_init(abnn_handle* h, const void* id128)
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     NC(ncclCommInitRank(&h->comm, (int)h->p.world_size, id, (int)h->p.rank));
-    if (tune_env("ABNN_P2P_EXCHANGE")) RET(p2p_setup(h));     // experiment, not measured yet: peer-memory exchange instead of NCCL
+    if (h->p.exchange == ABNN_EXCHANGE_PEER) RET(p2p_setup(h));   // peer-memory exchange instead of the NCCL allgather
     return 0;
 }
 
@@ -903,12 +912,22 @@ int abnn_load_bnn(abnn_handle* h, const char* path)
     if (!f) return fail(ABNN_ERR_IO, std::string("cannot open: ") + path);
     uint32_t hdr[2] = {0, 0};
     if (std::fread(hdr, 4, 2, f) != 2) { std::fclose(f); return fail(ABNN_ERR_IO, "short header"); }
-    if (!(hdr[0] == h->p.n_syn && hdr[1] == h->N)) {                                            // brain.cpp:174
+    // brain.cpp:174 rejects a file whose counts differ from the compiled-in shape. The neuron count must match here too;
+    // the record count may be anything the handle can hold (abnn_save_bnn writes the LIVE count, which pruning and
+    // synaptogenesis move away from n_syn).
+    if (hdr[1] != h->N) {
         std::fclose(f);
-        return fail(ABNN_ERR_SHAPE, ".bnn header (N_SYN, N_NRN) does not match the handle's shape");
+        return fail(ABNN_ERR_SHAPE, ".bnn header N_NRN does not match the handle's shape");
     }
     const u64 n = hdr[0], chunk = 4ull << 20;
-    if (n > h->cap) { std::fclose(f); return fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded"); }
+    if (n > h->cap) { std::fclose(f); return fail(ABNN_ERR_SHAPE, ".bnn header N_SYN exceeds the handle's synapse capacity"); }
+    {   // the whole table must be there before the device table is touched
+        const long at = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        const long end = std::ftell(f);
+        std::fseek(f, at, SEEK_SET);
+        if (at < 0 || end < 0 || (u64)(end - at) < n * sizeof(abnn_synapse)) { std::fclose(f); return fail(ABNN_ERR_IO, "short file: fewer records than the header announces"); }
+    }
     std::vector<abnn_synapse> buf(std::min<u64>(chunk, std::max<u64>(n, 1)));
     for (u64 off = 0; off < n; off += chunk) {
         const u64 m = std::min(chunk, n - off);
@@ -1012,6 +1031,30 @@ int abnn_load_state(abnn_handle* h, const char* path)
     std::vector<u64> counts(h->p.world_size);
     if (!rc && !(get(f, &saved, sizeof saved) && get(f, &sc, sizeof sc) && get(f, counts.data(), counts.size() * sizeof(u64))))
         rc = fail(ABNN_ERR_IO, "short read");
+    // The fields that define WHAT the saved state means must equal the handle's: the table is stored in table order (a
+    // GIVEN-order table in a sorted handle would break the sorted insertion of later growth steps), the event stream
+    // continues from the saved counters under the same sampler and seed, timestamps are in the saved clock's ticks.
+    // Execution mode, learning rates and placement may differ (a PARALLEL run can be resumed in EXACT mode).
+    if (!rc) {
+        const abnn_params& a = saved; const abnn_params& b = h->p;
+        if (a.sampler != b.sampler || a.release_rng != b.release_rng || a.clock_mode != b.clock_mode || a.src_view != b.src_view ||
+            a.rbar_mode != b.rbar_mode || a.sample_block != b.sample_block || a.table_order != b.table_order || a.seed != b.seed ||
+            a.window_pre != b.window_pre || a.refractory != b.refractory || a.teacher_gap != b.teacher_gap ||
+            a.max_spikes_per_pass != b.max_spikes_per_pass || a.track_visits != b.track_visits || a.n_input != b.n_input ||
+            a.n_hidden != b.n_hidden)
+            rc = fail(ABNN_ERR_SHAPE, ".bnn v2 was written under different semantics (sampler / sample_block / table_order / clock / src view / "
+                                      "r-bar mode / seed / window / refractory / budget / visits / shape differ from the handle's)");
+    }
+    if (!rc) {   // everything the rest of the file must hold, checked before any device state is overwritten
+        const size_t no_ = h->p.n_output;
+        const u64 need = (u64)(3 + h->p.fir_size) * no_ * sizeof(float) + (u64)(hd.snapshot ? 3 : 2) * h->N * sizeof(u64) +
+                         (u64)hd.grow_count * sizeof(GrowCand) + hd.n_local * sizeof(abnn_synapse);
+        const long at = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        const long end = std::ftell(f);
+        std::fseek(f, at, SEEK_SET);
+        if (at < 0 || end < 0 || (u64)(end - at) < need) rc = fail(ABNN_ERR_IO, ".bnn v2 file is shorter than its header announces");
+    }
     std::vector<char> buf(64u << 20);
     const size_t no = h->p.n_output;
     if (!rc) rc = file_to_dev(h, f, h->rs.rate, no * sizeof(float), buf);
@@ -1029,6 +1072,7 @@ int abnn_load_state(abnn_handle* h, const char* path)
         return fail(ABNN_ERR_CUDA, "device write failed during load");
     h->n_local = hd.n_local; h->n_local_all = counts; h->counts_dirty = false;
     h->slack_ready = false; h->fire_ready = false; h->view_stale = false;
+    if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }
     return 0;
 }
 
@@ -1046,7 +1090,7 @@ const Field kFields[] = {
     FLD(eta_reward, F_F32), FLD(alpha_rbar, F_F32), FLD(w_prune, F_F32), FLD(p_new, F_F32), FLD(w_init, F_F32),
     FLD(rate_alpha, F_F32), FLD(peak_decay, F_F32), FLD(peak_init, F_F32), FLD(use_fir, F_U32), FLD(fir_size, F_U32),
     FLD(reward_window, F_U32), FLD(filter_tau, F_F64), FLD(dt_sec, F_F64), FLD(loss0, F_F64), FLD(device, F_I32),
-    FLD(l2_persist, F_U32), FLD(sample_block, F_U32), FLD(table_order, F_U32),
+    FLD(l2_persist, F_U32), FLD(sample_block, F_U32), FLD(table_order, F_U32), FLD(prune_in_place, F_U32), FLD(exchange, F_U32),
 };
 #undef FLD
 std::string trim(const std::string& s)
@@ -1405,22 +1449,28 @@ int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out)
 {
     *list_out = h->d.grow; *owned_out = 0;
     DevScalars sc; RET(read_scalars(h, &sc));
-    if (sc.grow_overflow) {
-        k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
-        return fail(ABNN_ERR_CAPACITY, "growth staging buffer overflowed; call abnn_prune_and_grow more often");
-    }
-    u32 n = sc.grow_count;
+    bool overflow = sc.grow_overflow != 0;
+    u32 n = std::min(sc.grow_count, h->grow_cap);
     GrowCand* list = h->d.grow;
     u32 total = n;
+    std::vector<u64> cnt(h->p.world_size);
     if (h->p.world_size > 1) {
         if (!h->comm) return fail(ABNN_ERR_COMM, "world_size > 1 but abnn_comm_init has not been called");
-        // every rank needs everyone's candidates: exchange counts, pad to the maximum, allgather
-        u64 mine = n;
+        // every rank needs everyone's candidates: exchange counts — with this rank's overflow flag in the top bit, so that
+        // the ranks AGREE on the error before any of them leaves the collective sequence — pad to the maximum, allgather
+        const u64 mine = (u64)n | (overflow ? 1ull << 63 : 0);
         CU(cudaMemcpyAsync(h->d_counts + h->p.rank, &mine, sizeof(u64), cudaMemcpyHostToDevice, h->st));
         NC(ncclAllGather(h->d_counts + h->p.rank, h->d_counts, 1, ncclUint64, h->comm, h->st));
-        std::vector<u64> cnt(h->p.world_size);
         CU(cudaMemcpyAsync(cnt.data(), h->d_counts, sizeof(u64) * h->p.world_size, cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
+        for (u64& c : cnt) { if (c >> 63) overflow = true; c &= ~(1ull << 63); }
+    }
+    if (overflow) {                                          // the same status on every rank; the staged candidates are dropped
+        k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
+        CU(cudaStreamSynchronize(h->st));
+        return fail(ABNN_ERR_CAPACITY, "growth staging buffer overflowed on a rank (candidates of this interval are dropped); call abnn_prune_and_grow more often");
+    }
+    if (h->p.world_size > 1) {
         u32 maxc = 0;
         for (u64 c : cnt) maxc = std::max<u32>(maxc, (u32)c);
         total = maxc * h->p.world_size;
@@ -1475,7 +1525,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
         // 1. prune: stable compaction — into the spare table (count pass + scatter pass, no chained scan) when there is
         //    memory for one, else in place (k_compact)
         if (prune) {
-            static const bool in_place_only = tune_env("ABNN_PRUNE_IN_PLACE") != nullptr;   // measurements only
+            const bool in_place_only = h->p.prune_in_place != 0;
             const bool two_tables = 2 * h->cap * sizeof(abnn_synapse) <= h->mem_total / 2;
             abnn_synapse* spare = nullptr;
             if (!in_place_only && (h->d_spare || two_tables)) {

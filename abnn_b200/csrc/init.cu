@@ -1,7 +1,10 @@
 // abnn_b200/csrc/init.cu — device-side graph initialisation (README.md:134-135: Erdős–Rényi endpoints,
 // weights ~ Beta(2,8)). Edge g is a pure function of (seed, g): four Philox calls give src, dst and
 // nine uniforms; w is their 2nd smallest (the a-th order statistic of a+b-1 uniforms is Beta(a,b)),
-// so the table is reproducible on any device count and needs no transcendental functions.
+// so the table needs no transcendental functions and is reproducible for a given (seed, world_size): rank r generates
+// the edge ids [n*r/W, n*(r+1)/W) with dst uniform over ITS OWN neuron slice, i.e. the graph — and with it every result
+// of a sharded run — depends on the world size (a W-rank run is compared with the W-shard oracle, never with the
+// single-GPU run; include/abnn.h, "GPU-count invariance").
 // The reference's own build_random_graph (brain-engine.cpp:31-53) depends on the host C++ library's
 // mt19937 distributions and is therefore generated on the host (capi.cu) and uploaded.
 #include "common.cuh"

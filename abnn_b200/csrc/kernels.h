@@ -94,8 +94,8 @@ cudaError_t launch_sort_by_dst(abnn_synapse* syn, abnn_synapse* alt, u32* keys, 
                                void* tmp, size_t tmp_bytes, bool* result_in_alt, cudaStream_t st);
 
 // ABNN_TABLE_DST_INTERLEAVED: the dst-sorted table `in` (n records, destinations in [lo, lo + span)) interleaved per group of
-// 8 neurons into `out` (must not alias); start: span + 1 u64 of scratch (run starts).
-cudaError_t launch_interleave_by_dst(const abnn_synapse* in, abnn_synapse* out, u64 n, u32 lo, u32 span, u64* start, cudaStream_t st);
+// `group` (8 or 16) neurons into `out` (must not alias); start: span + 1 u64 of scratch (run starts).
+cudaError_t launch_interleave_by_dst(const abnn_synapse* in, abnn_synapse* out, u64 n, u32 lo, u32 span, u32 group, u64* start, cudaStream_t st);
 
 // Stable insertion of m new records (sorted by dst, ties in append order) into the dst-sorted table of n records,
 // out of place: out[0 .. n+m). cnt: dst_span + 1 zeroed u32 slots (per-neuron histogram -> prefix sums).

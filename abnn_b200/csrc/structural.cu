@@ -301,34 +301,36 @@ __global__ void __launch_bounds__(256) k_run_starts(const abnn_synapse* __restri
 }
 // Record i of the sorted table (destination d, r-th of its run) lands behind the rows 0..r-1 of its group of 8 neurons and
 // the row-r records of the group's lower destinations: base + sum_k min(c_k, r) + #{k < d & 7 : c_k > r}.
+template <u32 G>
 __global__ void __launch_bounds__(256) k_interleave(const abnn_synapse* __restrict__ in, abnn_synapse* __restrict__ out, u64 n, u32 lo,
                                                     u32 span, const u64* __restrict__ start)
 {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const uint4 rec = __ldcs(reinterpret_cast<const uint4*>(in + i));
-        const u32 d = rec.y, g0 = d & ~7u;                              // groups are aligned on the GLOBAL neuron id
+        const u32 d = rec.y, g0 = d & ~(G - 1u);                        // groups are aligned on the GLOBAL neuron id
         const u64 r = i - start[d - lo];
         u64 pos = 0, base = 0;
         bool have_base = false;
 #pragma unroll
-        for (u32 k = 0; k < 8; ++k) {
+        for (u32 k = 0; k < G; ++k) {
             const u32 nid = g0 + k;
             if (nid < lo || nid - lo >= span) continue;
             const u64 b = start[nid - lo], c = start[nid - lo + 1] - b;
             if (!have_base) { base = b; have_base = true; }
             pos += c < r ? c : r;
-            if (k < (d & 7u) && c > r) ++pos;
+            if (k < (d & (G - 1u)) && c > r) ++pos;
         }
         __stcs(reinterpret_cast<uint4*>(out + base + pos), rec);
     }
 }
-cudaError_t launch_interleave_by_dst(const abnn_synapse* in, abnn_synapse* out, u64 n, u32 lo, u32 span, u64* start, cudaStream_t st)
+cudaError_t launch_interleave_by_dst(const abnn_synapse* in, abnn_synapse* out, u64 n, u32 lo, u32 span, u32 group, u64* start, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
     u64 blocks = (n + 256) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_run_starts<<<(unsigned)blocks, 256, 0, st>>>(in, n, lo, span, start);
-    k_interleave<<<(unsigned)blocks, 256, 0, st>>>(in, out, n, lo, span, start);
+    if (group == 16) k_interleave<16><<<(unsigned)blocks, 256, 0, st>>>(in, out, n, lo, span, start);
+    else k_interleave<8><<<(unsigned)blocks, 256, 0, st>>>(in, out, n, lo, span, start);
     return cudaGetLastError();
 }
 

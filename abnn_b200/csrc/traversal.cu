@@ -710,6 +710,19 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
 // (common.cuh:release_word).
 // SB = sample_block: 8 (one 128-byte line per draw) or 16 (two consecutive lines = 256 bytes per draw, the size at which
 // random HBM3e reads reach the copy bandwidth: 6.7 TB/s against 4.7 TB/s for single lines, profiles/r2_notes.md).
+// Shared memory of a warp: the 4 KB stage, then the records of the chunk's OPEN events compacted in event order (16 B
+// each: src, dst, w, fire word). With the open events copied out, the stage is free as soon as phase B is over, and the
+// NEXT chunk's lines are requested before the dense steps run: the HBM latency of chunk c+1 hides under phase C of chunk
+// c (the kernel is latency-bound: 32 warps per SM, every warp alternates between waiting for its lines and working on
+// them). A chunk with more than LINE32_CQ open events is handled in place (stage read by the dense steps, copy issued
+// afterwards) — 96 covers the benchmark's regime (72 +- 7 open events per chunk) and keeps shared memory at 47 KB per CTA.
+#ifndef ABNN_LINE_CQ
+#define ABNN_LINE_CQ 96
+#endif
+constexpr u32 LINE32_CQ = ABNN_LINE_CQ;
+constexpr size_t LINE32_WARP_SMEM = LINE_STAGE_BYTES + LINE32_CQ * 16 + 256 + LINE_FIRE_CAP * sizeof(u32);   // 5952
+constexpr size_t LINE32_SMEM = LINE_WARPS * LINE32_WARP_SMEM;
+
 template <int VISITS, int GROW, int SB>
 __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_traverse_line32(const __grid_constant__ KParams kp, const DevPtrs d)
 {
@@ -719,8 +732,9 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* stage = line_smem + warp * LINE_WARP_SMEM;
-    unsigned char* queue = stage + LINE_STAGE_BYTES;
+    unsigned char* stage = line_smem + warp * LINE32_WARP_SMEM;
+    uint4* cq = reinterpret_cast<uint4*>(stage + LINE_STAGE_BYTES);            // open events of the chunk: src, dst, w, fire word
+    unsigned char* queue = stage + LINE_STAGE_BYTES + LINE32_CQ * 16;          // their chunk-local event indices
     u32* fl_dst = reinterpret_cast<u32*>(queue + 256);             // destinations that fired in this chunk
     const unsigned char* mine = stage + lane * 16;
     const u32 mine_addr = (u32)__cvta_generic_to_shared(mine);
@@ -761,23 +775,36 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         if (lane == 0) t = atomicAdd(&d.sc->chunk_ticket, 1u);
         return static_rounds * warps_total + __shfl_sync(0xffffffffu, t, 0);
     };
-    u32 c = take();
-    u64 m = draw(c, zw);
-    while (c < n_chunks) {
-        // ---- stage the chunk ------------------------------------------------------------------------
-        u32 okm = 0;
+    // request the lines of a chunk (8 LDGSTS.128 per lane, each warp instruction moves 4 whole lines); bit k of the result:
+    // this lane's record of step k exists
+    auto stage_issue = [&](u64 mm) -> u32 {
+        u32 ok = 0;
 #pragma unroll
         for (int k = 0; k < B; ++k) {
-            const u64 mk = __shfl_sync(0xffffffffu, m, k * 4 + sub);
+            const u64 mk = __shfl_sync(0xffffffffu, mm, k * 4 + sub);
             if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u)) {
-                okm |= 1u << k;
+                ok |= 1u << k;
                 cp_async16(mine_addr + k * 512, d.syn + (mk & ~7ull) + rec);
             }
         }
         cp_async_commit();
-        // two groups of the chunk drew the same line (small tables only): the later one re-reads the weights
-        const unsigned same = __match_any_sync(0xffffffffu, m);
-        const unsigned dupm = __ballot_sync(0xffffffffu, m != ~0ull && (same & lt) != 0);
+        return ok;
+    };
+    // bit g: line g of the chunk repeats an earlier line of the chunk (the later copy must see the weights the earlier one
+    // wrote). Only tables below 2^24 lines are checked: beyond that a repeat inside a chunk has probability < 3e-5 and
+    // means one event reading a weight that a concurrent event is updating — the race PARALLEL execution has between
+    // warps anyway.
+    const bool check_dups = kp.n_blocks < (1ull << 24);
+    auto dup_mask = [&](u64 mm) -> unsigned {
+        if (!check_dups) return 0u;
+        const unsigned same = __match_any_sync(0xffffffffu, mm);
+        return __ballot_sync(0xffffffffu, mm != ~0ull && (same & lt) != 0);
+    };
+    u32 c = take();
+    u64 m = draw(c, zw);
+    u32 okm = stage_issue(m);
+    unsigned dupm = dup_mask(m);
+    while (c < n_chunks) {
         const u32 c_next = take();
         const u64 m_next = draw(c_next, zw_next);            // ALU work under the copy's latency
         const u32 ev0 = c * (32u * B);                       // first event of the chunk (local index)
@@ -833,9 +860,13 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 const bool open = ((candm >> k) & 1u) && (u32)(gap < 0 ? -gap : gap) > refr;   // brain.metal:79-83
                 const unsigned cm = __ballot_sync(0xffffffffu, open);
                 if (open) {
-                    queue[nC + __popc(cm & lt)] = (unsigned char)(k * 32 + lane);
-                    // the fire word travels to the dense step in the record's unused pad slot of the stage
-                    *reinterpret_cast<int*>(const_cast<unsigned char*>(mine) + k * 512 + 12) = fire[j];
+                    const u32 pos = nC + __popc(cm & lt);
+                    queue[pos] = (unsigned char)(k * 32 + lane);
+                    if (pos < LINE32_CQ) {                   // the record leaves the stage, with the fire word in its unused pad slot
+                        uint4 r = *reinterpret_cast<const uint4*>(mine + k * 512);
+                        r.w = (u32)fire[j];
+                        cq[pos] = r;
+                    }
                 }
                 nC += __popc(cm);
             }
@@ -843,14 +874,19 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         n_cand += __popc(candm);
         __syncwarp();
 
+        // the open events are out of the stage: the next chunk's lines can come in while the dense steps run
+        const bool early = nC <= LINE32_CQ;
+        u32 okm_next = 0; unsigned dupm_next = 0;
+        if (early) { okm_next = stage_issue(m_next); dupm_next = dup_mask(m_next); }
+
         // ---- C: dense steps over the queue ----------------------------------------------------------------
         u32 nf = 0;                                          // destinations that fired in this chunk so far (warp-uniform)
-        bool spilled = false;
+        bool spilled = !early;                               // in place: the fire word is re-read (the stage copy holds none)
         u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0);            // sy.w = fire32[dst] as read in phase A
         bool cand = lane < nC;
         if (cand) {
             le = queue[lane];
-            sy = *reinterpret_cast<const uint4*>(stage + le * 16);                          // brain.metal:70
+            sy = early ? cq[lane] : *reinterpret_cast<const uint4*>(stage + le * 16);      // brain.metal:70
         }
         u32 j = 0;
 #pragma unroll 1
@@ -859,7 +895,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             const bool cand_n = j + 32 + lane < nC;
             if (cand_n) {                                    // next step's record
                 le_n = queue[j + 32 + lane];
-                sy_n = *reinterpret_cast<const uint4*>(stage + le_n * 16);
+                sy_n = early ? cq[j + 32 + lane] : *reinterpret_cast<const uint4*>(stage + le_n * 16);
             }
             const u32 g = le >> LOGB, r8 = le & 7u;
             const u64 edge = (__shfl_sync(0xffffffffu, m, g) & ~7ull) + r8;
@@ -891,16 +927,16 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                                                                     : u01_24(release_word((u32)zwg, SB, (g % LPG) * B + r8));
                 want = !skip && release_test(kp, w, u);                                     // brain.metal:91-92
             }
-            // in-warp order: the first event of a destination that fires blocks its later events (see header)
-            const unsigned cmask = __ballot_sync(0xffffffffu, cand);
-            const unsigned wm = __ballot_sync(0xffffffffu, want);
-            bool fired = false, gated = false;
-            if (cand) {
-                const unsigned F = wm & __match_any_sync(cmask, sy.y);
-                const int first = F ? __ffs(F) - 1 : 32;
-                fired = want && (int)lane == first;
-                gated = !skip && (int)lane <= first;
+            // in-warp order: the first event of a destination that fires blocks its later events (see header). An event is
+            // blocked iff an EARLIER lane of the step wants to fire on the same destination (the earliest such lane does
+            // fire); one shuffle per wanting lane (1-2 per step) instead of a match.any over up to 32 distinct destinations.
+            bool blocked = false;
+            for (unsigned wm = __ballot_sync(0xffffffffu, want); wm; wm &= wm - 1) {
+                const int wl = __ffs(wm) - 1;
+                const u32 dw = __shfl_sync(0xffffffffu, sy.y, wl);
+                blocked = blocked || (dw == sy.y && (int)lane > wl);
             }
+            const bool fired = want && !blocked, gated = cand && !skip && !blocked;
             if (gated) {
                 float isi = (float)(u32)(gap < 0 ? -gap : gap);                             // brain.metal:116 (now - ld)
                 if (fv == FIRE32_ANCIENT || fv == FIRE32_FUTURE) {   // beyond 2^30 ticks: the exact inter-spike interval
@@ -929,12 +965,13 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 cand = j + lane < nC;
                 if (cand) {
                     le = queue[j + lane];
-                    sy = *reinterpret_cast<const uint4*>(stage + le * 16);
+                    sy = early ? cq[j + lane] : *reinterpret_cast<const uint4*>(stage + le * 16);
                 }
             }
         }
-        __syncwarp();                                        // every lane is done with the stage
-        c = c_next; m = m_next; zw = zw_next;
+        __syncwarp();                                        // every lane is done with the stage and the queues
+        if (!early) { okm_next = stage_issue(m_next); dupm_next = dup_mask(m_next); }
+        c = c_next; m = m_next; zw = zw_next; okm = okm_next; dupm = dupm_next;
     }
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
 }
@@ -1087,22 +1124,25 @@ static cudaError_t launch_line32(const KParams& kp, const DevPtrs& d, int sm_cou
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_traverse_line32<VISITS, GROW, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(k_traverse_line32<VISITS, GROW, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINE32_SMEM);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     if (!kp.count || !kp.n_local) return cudaSuccess;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line32<VISITS, GROW, SB>, LINE_WARPS * 32, LINE_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line32<VISITS, GROW, SB>, LINE_WARPS * 32, LINE32_SMEM);
     if (per_sm < 1) per_sm = 1;
     const u64 chunks = (kp.count + 255) / 256;
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
-    // events in flight at once execute unordered: keep that window below a quarter of the refractory period (launch_line)
-    u64 lim = kp.refractory / (256ull * kp.world) / (4 * LINE_WARPS);
+    // Events in flight at once execute unordered; the one cross-warp order the semantics depend on is the refractory gate,
+    // and this kernel tests it against the fire word read at the START of a chunk: keep the in-flight window below 1/16 of
+    // the refractory period (measured at the 10k-neuron toy shape, fired count against the oracle: +4.3 % with a quarter of
+    // the period in flight, profiles/r2_notes.md). No limit in practice at the benchmark shape (period = 2 passes).
+    u64 lim = kp.refractory / (256ull * kp.world) / (16 * LINE_WARPS);
     if (lim < 1) lim = 1;
     if (grid > lim) grid = lim;
-    k_traverse_line32<VISITS, GROW, SB><<<(unsigned)grid, LINE_WARPS * 32, LINE_SMEM, st>>>(kp, d);
+    k_traverse_line32<VISITS, GROW, SB><<<(unsigned)grid, LINE_WARPS * 32, LINE32_SMEM, st>>>(kp, d);
     return cudaGetLastError();
 }
 

@@ -86,7 +86,8 @@ enum abnn_table_order {     /* HBM layout of this rank's synapse table          
                                  the table (sample_block = 8) touches one lastFired/lastVisited sector
                                  instead of eight. Table order is part of the semantics (edge(e) indexes
                                  it); the oracle applies the same stable sort.                  */
-    ABNN_TABLE_DST_INTERLEAVED = 2 /* DST_SORTED with the records of every group of 8 consecutive neurons (id >> 3)
+    ABNN_TABLE_DST_INTERLEAVED = 2 /* DST_SORTED with the records of every group of 8 consecutive neurons (id >> 3; 16
+                                 neurons when sample_block >= 16, so that a 256-byte sample group spans 16 neurons)
                                  interleaved: inside a group the order is (rank of the record among its
                                  destination's records, destination), i.e. row r of a group holds the r-th record
                                  of each of its neurons. A 128-byte line still touches ONE sector of the per-neuron
@@ -95,6 +96,12 @@ enum abnn_table_order {     /* HBM layout of this rank's synapse table          
                                  DST_SORTED its events arrive in bursts of sample_block, which lowers the fire rate
                                  by a few per cent — DESIGN.md §2). Re-derived after every upload / init / load
                                  and after every structural step that changed the table.        */
+};
+enum abnn_exchange {        /* per-pass timestamp exchange of a sharded handle (world_size > 1)          */
+    ABNN_EXCHANGE_NCCL = 0,   /*  ncclAllGather of the owned slices                       */
+    ABNN_EXCHANGE_PEER = 1    /*  each rank stores its slice of gate words straight into every peer's array over NVLink
+                                 (CUDA-IPC mappings, flag rounds instead of a collective; falls back to NCCL on every
+                                 rank if any rank cannot map a peer). Needs all ranks on one NVLink/NVSwitch node. */
 };
 enum abnn_profile {
     ABNN_PROFILE_METAL_PARITY = 0, /* SWEEP, XORSHIFT, PER_PASS, SERIAL, LIVE, METAL_TID0, budget 2560 */
@@ -174,7 +181,10 @@ typedef struct abnn_params {
      * Power of two, <= 32. Every edge is still sampled with equal probability. */
     uint32_t sample_block;
     uint32_t table_order;          /* abnn_table_order                                          */
-    uint32_t reserved_[2];
+    uint32_t prune_in_place;       /* 0: pruning compacts into a second table when the device has memory for one (count +
+                                      scatter passes, every tile independent), else in place; 1: always in place (single-
+                                      pass chained scan: no second table, about 1.7x slower)                          */
+    uint32_t exchange;             /* abnn_exchange: how sharded PARALLEL runs publish their gate words after a pass    */
 } abnn_params;
 
 #define ABNN_MAX_FIR 64u

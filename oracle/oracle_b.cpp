@@ -123,10 +123,12 @@ void sort_table(ob_handle* h)
     for (const auto& s : h->syn) out[start[s.dst - h->lo]++] = s;
     h->syn.swap(out);
     if (h->p.table_order != ABNN_TABLE_DST_INTERLEAVED) return;
+    // neurons per group = records per sample group (8, or 16 for sample_block >= 16): no two events of a group share a neuron
+    const uint64_t G = h->p.sample_block >= 16 ? 16 : 8;
     uint64_t o = 0;
-    for (uint64_t g0 = h->lo & ~7ull; g0 < h->hi; g0 += 8) {      // groups are aligned on the GLOBAL neuron id
-        uint64_t cnt[8], beg[8], rows = 0;
-        for (uint64_t k = 0; k < 8; ++k) {
+    for (uint64_t g0 = h->lo & ~(G - 1); g0 < h->hi; g0 += G) {   // groups are aligned on the GLOBAL neuron id
+        uint64_t cnt[16], beg[16], rows = 0;
+        for (uint64_t k = 0; k < G; ++k) {
             const uint64_t nid = g0 + k;
             const bool mine = nid >= h->lo && nid < h->hi;
             beg[k] = mine ? first[nid - h->lo] : 0;
@@ -134,7 +136,7 @@ void sort_table(ob_handle* h)
             rows = std::max(rows, cnt[k]);
         }
         for (uint64_t r = 0; r < rows; ++r)
-            for (uint64_t k = 0; k < 8; ++k)
+            for (uint64_t k = 0; k < G; ++k)
                 if (r < cnt[k]) out[o++] = h->syn[beg[k] + r];
     }
     h->syn.swap(out);

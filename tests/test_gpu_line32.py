@@ -84,7 +84,7 @@ def test_interleaved_table_single_warp_bit_exact(block):
         x.upload_synapses(syn); x.upload_timestamps(np.full(N, 1, np.uint64), None); x.clock = 1000; x.set_reward(0.2)
     assert b.download_synapses().tobytes() == o.download_synapses().tobytes(), "interleaved order differs after upload"
     t = b.download_synapses()["dst"]
-    assert len(set(t[800:808].tolist())) == 8                           # a line in the middle of the table: 8 different neurons
+    assert len(set(t[8000:8008].tolist())) == 8                         # a line in the middle of the table: 8 different neurons
     fired = 0
     for q in range(60):
         sb, so = b.run_pass(256), o.run_pass(256)

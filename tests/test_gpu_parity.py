@@ -510,29 +510,17 @@ def test_prune_compaction_is_stable_and_matches_oracle():
 
 
 def test_prune_compaction_in_place_path_matches_oracle():
-    """With room for a second table the prune goes out of place (count pass + scatter pass); the in-place single-pass
-    chained scan (k_compact) is what runs when the table takes more than a quarter of the device memory. The switch is
-    read once per process, so the in-place path is checked in a child process."""
-    import subprocess, sys, os
-    code = (
-        "import numpy as np\n"
-        "from abnn_b200 import Brain, capi\n"
-        "from oracle import pyoracle as O\n"
-        "from tests.helpers import random_graph\n"
-        "rng = np.random.default_rng(5)\n"
-        "n, N = 2_500_003, 40_000\n"
-        "syn = random_graph(rng, n, N, 0.0, 0.2)\n"
-        "p = O.default_params(capi.PROFILE_NORTH_STAR, n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, w_prune=0.07)\n"
-        "b, o = Brain(p), O.OracleB(p)\n"
-        "b.upload_synapses(syn); o.upload_synapses(syn)\n"
-        "sb, so = b.prune_and_grow(), o.prune_and_grow()\n"
-        "assert (sb.n_before, sb.pruned, sb.n_after) == (so.n_before, so.pruned, so.n_after) and so.pruned > 100000\n"
-        "assert b.download_synapses().tobytes() == o.download_synapses().tobytes()\n"
-        "print('ok')\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, ABNN_PRUNE_IN_PLACE="1"),
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+    """With room for a second table the prune goes out of place (count pass + scatter pass); params.prune_in_place = 1
+    selects the in-place single-pass chained scan (k_compact), which is also what runs when the table takes more than a
+    quarter of the device memory. Both must give the oracle's stable compaction."""
+    rng = np.random.default_rng(5)
+    n, N = 2_500_003, 40_000
+    syn = random_graph(rng, n, N, 0.0, 0.2)
+    b, o = pair(capi.PROFILE_NORTH_STAR, n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, w_prune=0.07, prune_in_place=1)
+    b.upload_synapses(syn); o.upload_synapses(syn)
+    sb, so = b.prune_and_grow(), o.prune_and_grow()
+    assert (sb.n_before, sb.pruned, sb.n_after) == (so.n_before, so.pruned, so.n_after) and so.pruned > 100000
+    assert b.download_synapses().tobytes() == o.download_synapses().tobytes()
 
 
 def test_structural_step_every_pass_fused_prune_merge_bit_exact():
