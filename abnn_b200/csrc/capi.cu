@@ -479,7 +479,11 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nul
 }
 
 // EXACT execution: phase 1 (candidates) -> radix sort by (dst, event) -> phase 3 (per-destination chains).
-int run_exact(abnn_handle* h, const KParams& kp)
+// The candidate count never leaves the device: the key buffer is padded to its capacity (= the events of the pass) with a
+// key that sorts behind every neuron, the sort always runs over the whole buffer, and phase 3 reads the count from device
+// memory — no host synchronisation inside a pass, so an EXACT pass can be enqueued asynchronously and captured into a
+// CUDA graph like a PARALLEL one. (Cost: a pass with few candidates still sorts `events` keys.)
+int ensure_exact_scratch(abnn_handle* h, const KParams& kp)
 {
     if (kp.count >= (1ull << 32)) return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution: at most 2^32-1 events per rank per pass");
     if (kp.count > h->x_cap) {
@@ -492,15 +496,18 @@ int run_exact(abnn_handle* h, const KParams& kp)
         CU(cudaMalloc(&h->d_xtmp, h->x_tmp_bytes ? h->x_tmp_bytes : 16));
         if (!h->d_xcount) CU(cudaMalloc(&h->d_xcount, sizeof(u32)));
         h->x_cap = cap;
+        if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old buffers
     }
+    return 0;
+}
+int run_exact(abnn_handle* h, const KParams& kp)
+{
+    RET(ensure_exact_scratch(h, kp));                 // no-op once the buffers fit (abnn_engine_step sizes them before a capture)
     if (!kp.count) return 0;
-    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, h->d_xvals, h->d_xcount, h->sm_count, h->st));
-    u32 n = 0;
-    CU(cudaMemcpyAsync(&n, h->d_xcount, sizeof(u32), cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));                 // the sort needs the item count on the host
-    int nb = 1; while ((1ull << nb) < h->N) ++nb;     // bits of a neuron id
-    CU(launch_exact_sort(h->d_xkeys, h->d_xvals, h->x_cap, n, 32 + nb, h->d_xtmp, h->x_tmp_bytes, h->st));
-    CU(launch_exact_phase3(kp, h->d, h->d_xkeys + h->x_cap, h->d_xvals + h->x_cap, h->d_xcount, n, h->sm_count, h->st));
+    int nb = 1; while ((1ull << nb) < h->N) ++nb;     // bits of a neuron id; the pad key's destination is 1 << nb
+    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, h->d_xvals, h->d_xcount, kp.count, nb, h->sm_count, h->st));
+    CU(launch_exact_sort(h->d_xkeys, h->d_xvals, h->x_cap, (u32)kp.count, 32 + nb + 1, h->d_xtmp, h->x_tmp_bytes, h->st));
+    CU(launch_exact_phase3(kp, h->d, h->d_xkeys + h->x_cap, h->d_xvals + h->x_cap, h->d_xcount, (u32)kp.count, h->sm_count, h->st));
     return 0;
 }
 
@@ -1318,15 +1325,15 @@ int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, flo
 
     const KParams kp = make_kparams(h, events);
     static const bool no_graph = tune_env("ABNN_NO_GRAPH") != nullptr;
-    // Single-GPU handles only: with the NCCL exchange inside the captured sequence a 2-rank run hung in
-    // this environment (NCCL 2.28.9, driver 580); sharded handles enqueue the same sequence eagerly.
-    // With the peer-memory exchange (p2p_setup) the sharded sequence holds no NCCL call once the gate words are being
-    // exchanged (slack_ready), so it can be captured too: opt-in on top of ABNN_P2P_EXCHANGE, not measured yet.
-    static const bool p2p_graph = tune_env("ABNN_P2P_GRAPH") != nullptr;
+    // Single-GPU handles, and sharded handles on the peer-memory exchange (params.exchange = ABNN_EXCHANGE_PEER) once the
+    // gate words are being exchanged (slack_ready): that sequence holds no NCCL call. With the NCCL exchange inside the
+    // captured sequence a 2-rank run hung in this environment (NCCL 2.28.9, driver 580); such handles enqueue eagerly.
     const bool pre[3] = {h->slack_ready, h->view_stale, h->fire_ready};
-    const bool sharded_ok = p2p_graph && h->p2p && pre[0] && slack_mode(h, kp) && h->slice >= (u64)h->p.n_input + h->p.n_output &&
+    const bool sharded_ok = h->p2p && pre[0] && slack_mode(h, kp) && h->slice >= (u64)h->p.n_input + h->p.n_output &&
                             !tune_env("ABNN_FULL_EXCHANGE");
-    const bool capturable = h->p.exec_mode == ABNN_EXEC_PARALLEL && (h->p.world_size == 1 || sharded_ok) && !no_graph;
+    const bool exact_ok = h->p.exec_mode == ABNN_EXEC_EXACT && h->p.world_size == 1;
+    if (exact_ok) RET(ensure_exact_scratch(h, kp));      // allocation must not happen inside a capture
+    const bool capturable = ((h->p.exec_mode == ABNN_EXEC_PARALLEL && (h->p.world_size == 1 || sharded_ok)) || exact_ok) && !no_graph;
     const bool match = h->step_exec && h->step_events == events && h->step_counts == h->n_local_all &&
                        h->step_pre[0] == pre[0] && h->step_pre[1] == pre[1] && h->step_pre[2] == pre[2];
     ++h->step_calls;

@@ -11,8 +11,10 @@
 //   phase 3  (parallel over destinations): one thread walks one destination's candidates in event order
 //                                          with lastFired[dst] in a register — exactly the serial loop
 //                                          restricted to that neuron.
-// The global spike budget is an ordered prefix over ALL events and is not supported here
-// (max_spikes_per_pass must be 0; use SERIAL for the budgeted metal-parity profile).
+// The global spike budget (brain.metal:85-98) is an ordered prefix over ALL events: the k-th fire in event order closes
+// the gate for every later event of every destination, which couples all the per-destination chains of phase 3. It is
+// not supported here (max_spikes_per_pass must be 0): SERIAL execution carries the budgeted metal-parity profile
+// bit-exactly, PARALLEL execution honours the budget with a saturating counter (tests/test_gpu_line32.py).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -145,8 +147,14 @@ size_t exact_sort_temp_bytes(u64 cap)
     return bytes;
 }
 
-// keys/vals: 2 x cap each ([0,cap) input, [cap,2cap) sorted output). n_host = candidate count (after phase 1).
-cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, u64* vals, u32* counter, int sm_count, cudaStream_t st)
+// keys/vals: 2 x cap each ([0,cap) input, [cap,2cap) sorted output).
+// k_exact_pad: keys[n .. n_slots) = a key behind every neuron's, n = the candidate count phase 1 left in *counter
+__global__ void __launch_bounds__(256) k_exact_pad(u64* keys, const u32* __restrict__ counter, u64 n_slots, u64 pad_key)
+{
+    for (u64 i = *counter + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) keys[i] = pad_key;
+}
+cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, u64* vals, u32* counter, u64 n_slots, int dst_bits,
+                                int sm_count, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(u32), st);
     if (e != cudaSuccess || !kp.count) return e;
@@ -154,6 +162,7 @@ cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, 
     const u64 cap = (u64)sm_count * 8;
     if (blocks > cap) blocks = cap;
     k_exact_phase1<<<(unsigned)blocks, 256, 0, st>>>(kp, d, keys, vals, counter);
+    k_exact_pad<<<(unsigned)blocks, 256, 0, st>>>(keys, counter, n_slots, ((1ull << dst_bits) << 32) | 0xFFFFFFFFull);
     return cudaGetLastError();
 }
 cudaError_t launch_exact_sort(u64* keys, u64* vals, u64 cap, u32 n, int key_bits, void* tmp, size_t tmp_bytes, cudaStream_t st)

@@ -35,7 +35,9 @@ cudaError_t launch_p2p_exchange(const KParams& kp, const DevPtrs& d, const P2PTa
 
 // exact.cu — EXACT execution (two-phase, bit-identical to SERIAL)
 size_t exact_sort_temp_bytes(u64 cap);
-cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, u64* vals, u32* counter, int sm_count, cudaStream_t st);
+// candidates into keys/vals[0 .. *counter), then keys[*counter .. n_slots) padded with a key whose destination is 1 << dst_bits
+cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* keys, u64* vals, u32* counter, u64 n_slots, int dst_bits,
+                                int sm_count, cudaStream_t st);
 cudaError_t launch_exact_sort(u64* keys, u64* vals, u64 cap, u32 n, int key_bits, void* tmp, size_t tmp_bytes, cudaStream_t st);
 cudaError_t launch_exact_phase3(const KParams& kp, const DevPtrs& d, const u64* keys_sorted, const u64* vals_sorted,
                                 const u32* counter, u32 n_host, int sm_count, cudaStream_t st);

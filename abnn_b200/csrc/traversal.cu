@@ -717,9 +717,13 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
 // them). A chunk with more than LINE32_CQ open events is handled in place (stage read by the dense steps, copy issued
 // afterwards) — 96 covers the benchmark's regime (72 +- 7 open events per chunk) and keeps shared memory at 47 KB per CTA.
 #ifndef ABNN_LINE_CQ
-#define ABNN_LINE_CQ 96
+#define ABNN_LINE_CQ 0
 #endif
-constexpr u32 LINE32_CQ = ABNN_LINE_CQ;
+#ifndef ABNN_LINE_EARLY
+#define ABNN_LINE_EARLY 1
+#endif
+constexpr u32 LINE32_CQ = ABNN_LINE_CQ;                    // 0: no compacted copy — the dense steps read the stage in place
+constexpr bool LINE32_EARLY = LINE32_CQ > 0 && ABNN_LINE_EARLY;
 constexpr size_t LINE32_WARP_SMEM = LINE_STAGE_BYTES + LINE32_CQ * 16 + 256 + LINE_FIRE_CAP * sizeof(u32);   // 5952
 constexpr size_t LINE32_SMEM = LINE_WARPS * LINE32_WARP_SMEM;
 
@@ -862,7 +866,9 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 if (open) {
                     const u32 pos = nC + __popc(cm & lt);
                     queue[pos] = (unsigned char)(k * 32 + lane);
-                    if (pos < LINE32_CQ) {                   // the record leaves the stage, with the fire word in its unused pad slot
+                    if (LINE32_CQ == 0) {                    // the fire word travels to the dense step in the record's unused pad slot
+                        *reinterpret_cast<int*>(const_cast<unsigned char*>(mine) + k * 512 + 12) = fire[j];
+                    } else if (pos < LINE32_CQ) {            // the record leaves the stage, with the fire word in its pad slot
                         uint4 r = *reinterpret_cast<const uint4*>(mine + k * 512);
                         r.w = (u32)fire[j];
                         cq[pos] = r;
@@ -875,18 +881,19 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         __syncwarp();
 
         // the open events are out of the stage: the next chunk's lines can come in while the dense steps run
-        const bool early = nC <= LINE32_CQ;
+        const bool in_cq = LINE32_CQ > 0 && nC <= LINE32_CQ;     // the dense steps read the compacted copy
+        const bool early = LINE32_EARLY && in_cq;
         u32 okm_next = 0; unsigned dupm_next = 0;
         if (early) { okm_next = stage_issue(m_next); dupm_next = dup_mask(m_next); }
 
         // ---- C: dense steps over the queue ----------------------------------------------------------------
         u32 nf = 0;                                          // destinations that fired in this chunk so far (warp-uniform)
-        bool spilled = !early;                               // in place: the fire word is re-read (the stage copy holds none)
+        bool spilled = LINE32_CQ > 0 && !in_cq;              // overflow of the compacted copy: in place, fire word re-read
         u32 le = 0; uint4 sy = make_uint4(0, 0, 0, 0);            // sy.w = fire32[dst] as read in phase A
         bool cand = lane < nC;
         if (cand) {
             le = queue[lane];
-            sy = early ? cq[lane] : *reinterpret_cast<const uint4*>(stage + le * 16);      // brain.metal:70
+            sy = in_cq ? cq[lane] : *reinterpret_cast<const uint4*>(stage + le * 16);      // brain.metal:70
         }
         u32 j = 0;
 #pragma unroll 1
@@ -895,7 +902,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             const bool cand_n = j + 32 + lane < nC;
             if (cand_n) {                                    // next step's record
                 le_n = queue[j + 32 + lane];
-                sy_n = early ? cq[j + 32 + lane] : *reinterpret_cast<const uint4*>(stage + le_n * 16);
+                sy_n = in_cq ? cq[j + 32 + lane] : *reinterpret_cast<const uint4*>(stage + le_n * 16);
             }
             const u32 g = le >> LOGB, r8 = le & 7u;
             const u64 edge = (__shfl_sync(0xffffffffu, m, g) & ~7ull) + r8;
@@ -965,7 +972,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 cand = j + lane < nC;
                 if (cand) {
                     le = queue[j + lane];
-                    sy = early ? cq[j + lane] : *reinterpret_cast<const uint4*>(stage + le * 16);
+                    sy = in_cq ? cq[j + lane] : *reinterpret_cast<const uint4*>(stage + le * 16);
                 }
             }
         }

@@ -115,7 +115,7 @@ def test_manifest_loader(tmp_path):
     assert (p.window_pre, tau_ltd.value, steps.value, p.seed) == (20_000, 40_000, 1_000_000, 42)
     assert (np.float32(p.a_ltp), np.float32(p.a_ltd)) == (np.float32(0.01), np.float32(0.005))
     assert (np.float32(p.w_min), np.float32(p.w_max)) == (np.float32(0.001), np.float32(1.0))      # nested w_max ignored
-    assert (p.sample_block, p.table_order) == (8, capi.TABLE_DST_SORTED)
+    assert (p.sample_block, p.table_order) == (8, capi.TABLE_DST_SORTED)                          # abnn_params field names as keys
     bad = tmp_path / "bad.yml"
     bad.write_text("synapses: lots\n")
     assert lib.abnn_params_from_manifest(str(bad).encode(), C.byref(p), None, None) == capi.ERR_INVALID
@@ -124,3 +124,24 @@ def test_manifest_loader(tmp_path):
     small.write_text("neurons: 100\n")
     assert lib.abnn_params_from_manifest(str(small).encode(), C.byref(p), None, None) == capi.ERR_INVALID
     assert lib.abnn_params_from_manifest(b"/nonexistent.yml", C.byref(p), None, None) == capi.ERR_IO
+
+
+def test_manifest_loader_on_the_reference_manifest():
+    """The reference's own abnn/manifests/simple.yml (read where it lies; present in the build container only): the ABNN keys
+    at :3-12 map as documented — values the reference's fkYAML-based loader returns as STRINGS (`20_000`) become numbers —
+    and the dense-NN blocks below them (layers / training / dataset) are skipped."""
+    ref = "/root/reference/abnn/manifests/simple.yml"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    lib = capi.load()
+    p = capi.default_params(capi.PROFILE_NORTH_STAR)
+    steps, tau_ltd = C.c_uint64(), C.c_uint64()
+    assert lib.abnn_params_from_manifest(ref.encode(), C.byref(p), C.byref(steps), C.byref(tau_ltd)) == 0, lib.abnn_last_error()
+    assert (p.n_input, p.n_output, p.n_hidden, p.n_syn) == (256, 256, 65536 - 512, 524288)         # neurons: 65536, synapses: 524288
+    assert (p.window_pre, tau_ltd.value, steps.value, p.seed) == (20_000, 40_000, 1_000_000, 42)   # tau_LTP / tau_LTD / steps / rng_seed
+    assert (np.float32(p.a_ltp), np.float32(p.a_ltd)) == (np.float32(0.01), np.float32(0.005))
+    assert (np.float32(p.w_min), np.float32(p.w_max)) == (np.float32(0.001), np.float32(1.0))
+    q = capi.default_params(capi.PROFILE_NORTH_STAR)                                                # nothing else moved
+    for name, _ in capi.Params._fields_:
+        if name not in ("n_hidden", "n_syn", "window_pre", "seed", "a_ltp", "a_ltd", "w_min", "w_max"):
+            assert getattr(p, name) == getattr(q, name), name

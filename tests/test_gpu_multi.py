@@ -59,9 +59,11 @@ def _gpu_worker(rank, world, port, exec_mode, q, refractory=None):
         dist.destroy_process_group()
 
 
-def _gate_worker(rank, world, port, q):
-    """PARALLEL line kernel on a dst-sorted table, sharded: after every pass the exchanged 32-bit gate words
-    must equal clamp(window_pre - (clock - lastFired) + 1) of the replicated lastFired on every rank."""
+def _gate_worker(rank, world, port, q, exchange=0, order=1, engine=False):
+    """PARALLEL line kernel on a dst-sorted / interleaved table, sharded: after every pass the exchanged 32-bit gate
+    words must equal clamp(window_pre - (clock - lastFired) + 1) of the replicated lastFired on every rank. exchange:
+    abnn_params.exchange (NCCL allgather or peer-memory stores); engine: drive the passes through abnn_engine_step (on
+    the peer exchange the sharded step is replayed from a CUDA graph from the third call on)."""
     import torch
     import torch.distributed as dist
     from abnn_b200 import distributed as D
@@ -69,26 +71,55 @@ def _gate_worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        scen = dict(SCEN, refractory=3_000, p_new=0.0, w_prune=0.0, table_order=capi.TABLE_DST_SORTED)
+        scen = dict(SCEN, refractory=3_000, p_new=0.0, w_prune=0.0, table_order=order, exchange=exchange)
         base = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_PARALLEL, **scen)
         b = D.create_sharded_brain(base, device=rank)
         N, syn, pre, frames = _inputs()
         b.upload_synapses(syn)
         b.upload_timestamps(pre, None); b.clock = 500_000; b.set_reward(0.2)
         out = []
-        for it, (vin, exp) in enumerate(frames):
-            b.inject_inputs(vin, 1000.0); b.teacher_force(exp, float(it & 1))
-            st = b.run_pass(300_000)
+        info = b.info()
+        for it, (vin, exp) in enumerate(frames + frames if engine else frames):
+            if engine:
+                b.engine_step(vin, exp, 1000.0, float(it & 1), 300_000)
+                ev, fired = 150_000, 1000                 # no per-pass statistics on this path
+            else:
+                b.inject_inputs(vin, 1000.0); b.teacher_force(exp, float(it & 1))
+                st = b.run_pass(300_000)
+                ev, fired = st.events, st.fired
             words, valid = b.gate_words()
             lf, lv = b.timestamps()                       # collective: refreshes the 64-bit snapshot
-            out.append((st.events, st.fired, valid, words.tobytes(), lf.tobytes(), b.clock, b.read_outputs().tobytes()))
+            out.append((ev, fired, valid, words.tobytes(), lf.tobytes(), b.clock, b.read_outputs().tobytes(),
+                        lv[info.neuron_lo:info.neuron_hi].tobytes()))
         q.put((rank, out))
         b.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpus_parallel_gate_word_exchange():
+def _oracle_visits(order, n_pass):
+    """lastVisited of the two-shard oracle after n_pass passes of the gate-word scenario (an order-free max over the
+    sampled events: the PARALLEL sharded run must reproduce it exactly, whatever the exchange)."""
+    from oracle import pyoracle as O
+    scen = dict(SCEN, refractory=3_000, p_new=0.0, w_prune=0.0, table_order=order)
+    world = O.OracleWorld(O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_SERIAL, **scen), 2)
+    N, syn, pre, frames = _inputs()
+    world.upload_synapses(syn)
+    for s in world.shards:
+        s.upload_timestamps(pre, None); s.clock = 500_000; s.set_reward(0.2)
+    out = []
+    for it, (vin, exp) in enumerate((frames + frames)[:n_pass]):
+        for s in world.shards:
+            s.inject_inputs(vin, 1000.0); s.teacher_force(exp, float(it & 1))
+        world.run_pass(300_000)
+        half = -(-N // 2)
+        out.append([s.timestamps()[1][k * half:min(N, (k + 1) * half)].tobytes() for k, s in enumerate(world.shards)])
+    return out
+
+
+@pytest.mark.parametrize("exchange,order,engine", [(0, 1, False), (1, 1, False), (1, 2, False), (1, 2, True), (0, 2, True)],
+                         ids=["nccl-sorted", "peer-sorted", "peer-interleaved", "peer-interleaved-graph", "nccl-interleaved-engine"])
+def test_two_gpus_parallel_gate_word_exchange(exchange, order, engine):
     import multiprocessing as mp
     import torch
     if torch.cuda.device_count() < 2:
@@ -96,15 +127,18 @@ def test_two_gpus_parallel_gate_word_exchange():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    procs = [ctx.Process(target=_gate_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gate_worker, args=(r, 2, port, q, exchange, order, engine)) for r in range(2)]
     [p.start() for p in procs]
     res = dict(q.get(timeout=300) for _ in procs)
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     W = SCEN["window_pre"]
     fired = 0
-    for it in range(4):
-        (ev0, f0, valid0, w0, lf0, c0, o0), (ev1, f1, valid1, w1, lf1, c1, o1) = res[0][it], res[1][it]
+    n_pass = 8 if engine else 4
+    visits = _oracle_visits(order, n_pass)
+    for it in range(n_pass):
+        assert res[0][it][7] == visits[it][0] and res[1][it][7] == visits[it][1], f"lastVisited differs from the two-shard oracle after pass {it}"
+        (ev0, f0, valid0, w0, lf0, c0, o0, _), (ev1, f1, valid1, w1, lf1, c1, o1, _) = res[0][it], res[1][it]
         assert valid0 and valid1, "the sharded PARALLEL exchange must deliver the gate words"
         assert w0 == w1 and lf0 == lf1 and c0 == c1 and o0 == o1, f"ranks disagree after pass {it}"
         lf = np.frombuffer(lf0, np.uint64).astype(np.int64)

@@ -360,6 +360,26 @@ def test_engine_step_graph_replay_is_bit_exact():
     assert b.get_loss() == o.get_loss() and o.get_loss()[1] == 2
 
 
+def test_engine_step_exact_mode_is_captured_and_bit_exact():
+    """EXACT execution keeps its candidate count on the device (padded sort), so abnn_engine_step records it into a CUDA
+    graph like a PARALLEL pass: line sampler over the interleaved table, conflicts and growth on, 8 engine steps — every
+    filtered read-out and the final state equal the oracle bit for bit."""
+    over = dict(n_input=64, n_output=64, n_hidden=3000, n_syn=120_000, exec_mode=capi.EXEC_EXACT, sample_block=8,
+                table_order=capi.TABLE_DST_INTERLEAVED, window_pre=400_000, refractory=20_000, p_new=0.05, reward_window=3,
+                syn_capacity=130_000)
+    b, o = pair(capi.PROFILE_NORTH_STAR, **over)
+    b.build_random_graph(1); o.init_graph(capi.GRAPH_REFERENCE, 1)
+    stim = FunctionalDataset(64, 64)
+    for p in range(8):
+        vin, exp = stim.nextInput(), stim.nextExpected()
+        rb = b.engine_step(vin, exp, 1000.0, float(p & 1), 100_000, want_rates=True)
+        o.inject_inputs(vin, 1000.0); o.teacher_force(exp, float(p & 1)); so = o.run_pass(100_000)
+        assert rb.tobytes() == o.readout_filtered(exp).tobytes(), f"pass {p}"
+    assert so.gated > 1000
+    assert_same_state(b, o, "after 8 EXACT engine steps")
+    assert b.get_loss() == o.get_loss() and o.get_loss()[1] == 2
+
+
 def test_parallel_statistical_parity_toy():
     """configs[0] at full size (1M synapses, 1M-event passes), fully parallel. Bounds: gated and fired
     counts within 6 % of the oracle's (+ 5 sigma Poisson; the library keeps at most 1/16 of a pass in

@@ -241,3 +241,55 @@ def test_oracle_b_matches_frozen_northstar_checksums(oracle):
     last = want["toy_line_sorted"][-1]
     assert last["stats"]["gated"] > 100_000 and last["stats"]["fired"] > 1000 and last["structural"]["pruned"] > 0
     assert want["toy_reference"][-1]["structural"]["appended"] > 0
+
+
+def test_logger_matches_the_reference_logger_byte_for_byte(tmp_path):
+    """abnn_b200::Logger (include/abnn_brain.hpp) against the reference's Logger compiled verbatim (logger.cpp:13-84 through
+    oracle/ref_pieces.cpp): the same script of 3 frames, 10 losses (the 10th truncates the file, logger.cpp:68), 1 more
+    frame; abnn_session.m must be byte-identical after EVERY call and the loss EMA must agree."""
+    import struct
+    import subprocess
+    from oracle import pyoracle as O
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built (needs the reference tree)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "logger_parity"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "host_cpp", "logger_parity.cpp"),
+                    "-o", str(exe), "-L", os.path.join(root, "abnn_b200"), "-labnn_b200", "-Wl,-rpath," + os.path.join(root, "abnn_b200"), "-pthread"],
+                   check=True, capture_output=True, text=True)
+    n_in, n_out = 12, 9
+    rng = np.random.default_rng(3)
+    ops = [("frame", rng.random(n_in).astype(np.float32) * 2 - 1, rng.random(n_out).astype(np.float32)) for _ in range(3)]
+    ops += [("loss", 0.25 / (l + 1)) for l in range(10)]
+    ops += [("frame", np.linspace(-1, 1, n_in).astype(np.float32), np.full(n_out, 1e-7, np.float32))]
+    script = tmp_path / "script.bin"
+    with open(script, "wb") as f:
+        for op in ops:
+            if op[0] == "frame":
+                f.write(struct.pack("<i", 0)); f.write(op[1].tobytes()); f.write(op[2].tobytes())
+            else:
+                f.write(struct.pack("<id", 1, op[1]))
+    ours = tmp_path / "ours.m"
+    r = subprocess.run([str(exe), str(ours), str(script), str(n_in), str(n_out)], capture_output=True, text=True, check=True)
+    ref_exe = tmp_path / "logger_ref_driver"
+    ref_lib_dir = os.path.dirname(O.LIB_P)
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "host_cpp", "logger_ref_driver.cpp"), "-o", str(ref_exe),
+                    O.LIB_P, "-Wl,-rpath," + ref_lib_dir], check=True, capture_output=True, text=True)
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    # the reference writes into its current directory (logger.cpp:14): a process of its own, started there
+    subprocess.run([str(ref_exe), str(script), str(n_in), str(n_out)], cwd=ref_dir, capture_output=True, text=True, check=True)
+    for k, op in enumerate(ops):
+        want = (ref_dir / f"ref.{k}").read_bytes()
+        got = (tmp_path / f"ours.m.{k}").read_bytes()
+        assert got == want, f"abnn_session.m differs after call {k} ({op[0]}): {len(got)} vs {len(want)} bytes"
+        if k == 2:
+            assert want.count(b"clf;") == 3
+        if k == 12:
+            assert want == b""                          # truncated by the 10th loss (logger.cpp:68); the new header is still buffered
+        if k == 13:
+            assert want.startswith(b"% ABNN animated session\n") and want.count(b"clf;") == 1
+    ema = 0.0
+    for l in range(10):
+        ema = 0.25 / (l + 1) if l == 0 else 0.98 * ema + (1.0 - 0.98) * 0.25 / (l + 1)          # logger.cpp:61-62
+    assert abs(float(r.stdout.strip().splitlines()[-1].split()[1]) - ema) < 1e-15
