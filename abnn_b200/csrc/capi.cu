@@ -550,7 +550,7 @@ int abnn_default_params(abnn_params* p, uint32_t profile)
     p->filter_tau = 0.02; p->dt_sec = 0.0009; p->loss0 = 0.25;
     p->device = -1; p->rank = 0; p->world_size = 1; p->l2_persist = 1;
     p->sample_block = 1;
-    if (profile == ABNN_PROFILE_B200) { p->sample_block = 8; p->table_order = ABNN_TABLE_DST_INTERLEAVED; }
+    if (profile == ABNN_PROFILE_B200) { p->sample_block = 16; p->table_order = ABNN_TABLE_DST_INTERLEAVED; }
     return 0;
 }
 

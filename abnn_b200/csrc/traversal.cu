@@ -722,23 +722,30 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
 #ifndef ABNN_LINE_EARLY
 #define ABNN_LINE_EARLY 1
 #endif
+#ifndef ABNN_LINE_STEPS
+#define ABNN_LINE_STEPS 8
+#endif
 constexpr u32 LINE32_CQ = ABNN_LINE_CQ;                    // 0: no compacted copy — the dense steps read the stage in place
 constexpr bool LINE32_EARLY = LINE32_CQ > 0 && ABNN_LINE_EARLY;
-constexpr size_t LINE32_WARP_SMEM = LINE_STAGE_BYTES + LINE32_CQ * 16 + 256 + LINE_FIRE_CAP * sizeof(u32);   // 5952
+constexpr int LINE32_STEPS = ABNN_LINE_STEPS;              // steps of 4 lines per chunk: a chunk is 4 * STEPS lines
+constexpr u32 LINE32_LPC = 4 * LINE32_STEPS, LINE32_EPC = 32 * LINE32_STEPS;
+constexpr size_t LINE32_STAGE = (size_t)LINE32_STEPS * 512;
+constexpr size_t LINE32_WARP_SMEM = LINE32_STAGE + LINE32_CQ * 16 + 256 + LINE_FIRE_CAP * sizeof(u32);
 constexpr size_t LINE32_SMEM = LINE_WARPS * LINE32_WARP_SMEM;
 
 template <int VISITS, int GROW, int SB>
 __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_traverse_line32(const __grid_constant__ KParams kp, const DevPtrs d)
 {
     constexpr int LOGB = 3, B = 8, PART = ABNN_LINE_PART;     // a LINE is 8 records; a sample group is LPG lines
-    constexpr int LPG = SB / 8, LOGSB = SB == 8 ? 3 : 4, GPC = 32 / LPG;
+    constexpr int LPG = SB / 8, LOGSB = SB == 8 ? 3 : 4;
     static_assert(SB == 8 || SB == 16, "line kernel: sample_block 8 or 16");
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NS = LINE32_STEPS;
     unsigned char* stage = line_smem + warp * LINE32_WARP_SMEM;
-    uint4* cq = reinterpret_cast<uint4*>(stage + LINE_STAGE_BYTES);            // open events of the chunk: src, dst, w, fire word
-    unsigned char* queue = stage + LINE_STAGE_BYTES + LINE32_CQ * 16;          // their chunk-local event indices
+    uint4* cq = reinterpret_cast<uint4*>(stage + LINE32_STAGE);                // open events of the chunk: src, dst, w, fire word
+    unsigned char* queue = stage + LINE32_STAGE + LINE32_CQ * 16;              // their chunk-local event indices
     u32* fl_dst = reinterpret_cast<u32*>(queue + 256);             // destinations that fired in this chunk
     const unsigned char* mine = stage + lane * 16;
     const u32 mine_addr = (u32)__cvta_generic_to_shared(mine);
@@ -750,7 +757,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     const u32 rec = lane & (B - 1), sub = lane >> LOGB;
     const unsigned lt = (1u << lane) - 1u;
     const u32 count = (u32)kp.count;                               // < 2^30 (ticks < 2^30)
-    const u32 n_chunks = (count + 32u * B - 1) / (32u * B);
+    const u32 n_chunks = (count + LINE32_EPC - 1) / LINE32_EPC;
     const u32 world = kp.world, refr = (u32)kp.refractory;
 
     // lane L holds LINE L of chunk c: m = line base (a multiple of 8) | (valid records - 1), ~0 = none; zw = .z | .w << 32 of
@@ -758,8 +765,8 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     // lanes of a group evaluate the group's draw (same warp instructions, no shuffle).
     u64 zw = 0, zw_next = 0;
     auto draw = [&](u32 c, u64& zw_out) -> u64 {
-        const u32 i0 = (c * GPC + (lane / LPG)) << LOGSB;    // first event of the line's group
-        if (c >= n_chunks || i0 >= count) return ~0ull;
+        const u32 i0 = (c * (LINE32_LPC / LPG) + (lane / LPG)) << LOGSB;    // first event of the line's group
+        if (c >= n_chunks || lane >= LINE32_LPC || i0 >= count) return ~0ull;
         const Philox4 r = event_philox(kp, event_base + i0);
         zw_out = (u64)r.z | ((u64)r.w << 32);
         const u64 be = mulhi64(((u64)r.x << 32) | r.y, kp.n_blocks) << LOGSB;
@@ -784,7 +791,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     auto stage_issue = [&](u64 mm) -> u32 {
         u32 ok = 0;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
+        for (int k = 0; k < NS; ++k) {
             const u64 mk = __shfl_sync(0xffffffffu, mm, k * 4 + sub);
             if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u)) {
                 ok |= 1u << k;
@@ -811,7 +818,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     while (c < n_chunks) {
         const u32 c_next = take();
         const u64 m_next = draw(c_next, zw_next);            // ALU work under the copy's latency
-        const u32 ev0 = c * (32u * B);                       // first event of the chunk (local index)
+        const u32 ev0 = c * LINE32_EPC;                      // first event of the chunk (local index)
         const u32 t0 = ev0 * world + kp.rank;                // its tick offset: now = clock + t
         cp_async_wait<0>();
         __syncwarp();
@@ -819,7 +826,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         // ---- A + B: gate words and fire32[dst] in flight, window test, visit, refractory prefilter, compaction ----
         u32 candm = 0, nC = 0;
 #pragma unroll
-        for (int k0 = 0; k0 < B; k0 += PART) {
+        for (int k0 = 0; k0 < NS; k0 += PART) {
             u32 gate[PART];
             int fire[PART];
             u32 exact = 0;
@@ -1139,14 +1146,14 @@ static cudaError_t launch_line32(const KParams& kp, const DevPtrs& d, int sm_cou
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse_line32<VISITS, GROW, SB>, LINE_WARPS * 32, LINE32_SMEM);
     if (per_sm < 1) per_sm = 1;
-    const u64 chunks = (kp.count + 255) / 256;
+    const u64 chunks = (kp.count + LINE32_EPC - 1) / LINE32_EPC;
     u64 grid = (u64)sm_count * per_sm;
     if (grid > (chunks + LINE_WARPS - 1) / LINE_WARPS) grid = (chunks + LINE_WARPS - 1) / LINE_WARPS;
     // Events in flight at once execute unordered; the one cross-warp order the semantics depend on is the refractory gate,
     // and this kernel tests it against the fire word read at the START of a chunk: keep the in-flight window below 1/16 of
     // the refractory period (measured at the 10k-neuron toy shape, fired count against the oracle: +4.3 % with a quarter of
     // the period in flight, profiles/r2_notes.md). No limit in practice at the benchmark shape (period = 2 passes).
-    u64 lim = kp.refractory / (256ull * kp.world) / (16 * LINE_WARPS);
+    u64 lim = kp.refractory / ((u64)LINE32_EPC * kp.world) / (16 * LINE_WARPS);
     if (lim < 1) lim = 1;
     if (grid > lim) grid = lim;
     k_traverse_line32<VISITS, GROW, SB><<<(unsigned)grid, LINE_WARPS * 32, LINE32_SMEM, st>>>(kp, d);

@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--syn", type=int, default=0, help="global synapse count (default: 1e9; --structural: 5e8 per GPU)")
     ap.add_argument("--events", type=int, default=150_000_000)
     ap.add_argument("--sampler", default="philox", choices=["philox", "sweep"])
-    ap.add_argument("--block", type=int, default=8, help="PHILOX sampler granularity in records (8 = one 128-byte HBM line per draw; 1 = iid)")
+    ap.add_argument("--block", type=int, default=16, help="PHILOX sampler granularity in records (16 = 256 bytes = two 128-byte HBM lines per draw; 1 = iid)")
     ap.add_argument("--table-order", default="interleaved", choices=list(TABLE_ORDERS),
                     help="interleaved = ABNN_TABLE_DST_INTERLEAVED (8 adjacent destinations per 128-byte line), dst = ABNN_TABLE_DST_SORTED "
                          "(stable sort by destination neuron), given = generation order")
@@ -612,7 +612,7 @@ def main():
             subs = {}
             for name, over in (("iid_sampler", dict(sample_block=1, table_order=capi.TABLE_AS_GIVEN)),
                                ("line8_dst_sorted", dict(sample_block=8, table_order=capi.TABLE_DST_SORTED)),
-                               ("block16_interleaved", dict(sample_block=16, table_order=capi.TABLE_DST_INTERLEAVED))):
+                               ("line8_interleaved", dict(sample_block=8, table_order=capi.TABLE_DST_INTERLEAVED))):
                 try:
                     subs[name] = sub_record(args, name, peak, **over)
                 except Exception as e:                # a sub-record must never take the headline down

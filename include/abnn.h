@@ -106,8 +106,9 @@ enum abnn_exchange {        /* per-pass timestamp exchange of a sharded handle (
 enum abnn_profile {
     ABNN_PROFILE_METAL_PARITY = 0, /* SWEEP, XORSHIFT, PER_PASS, SERIAL, LIVE, METAL_TID0, budget 2560 */
     ABNN_PROFILE_NORTH_STAR   = 1, /* PHILOX, PHILOX, PER_EVENT, PARALLEL, SNAPSHOT, PASS_STEP          */
-    ABNN_PROFILE_B200         = 2  /* NORTH_STAR with the layout the B200 kernel is built for: sample_block 8
-                                      (one 128-byte line per draw) over a DST_INTERLEAVED table — what bench.py times */
+    ABNN_PROFILE_B200         = 2  /* NORTH_STAR with the layout the B200 kernel is built for: sample_block 16 (256 bytes
+                                      = two 128-byte lines per draw, the size at which random HBM3e reads reach the copy
+                                      bandwidth) over a DST_INTERLEAVED table — what bench.py times                  */
 };
 
 /* ---- L3: every compile-time knob of the reference as a runtime parameter ------------------

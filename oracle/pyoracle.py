@@ -66,7 +66,7 @@ def default_params(profile: int = capi.PROFILE_NORTH_STAR, **over) -> capi.Param
     p.device, p.rank, p.world_size, p.l2_persist = -1, 0, 1, 1
     p.sample_block = 1
     if profile == capi.PROFILE_B200:
-        p.sample_block, p.table_order = 8, capi.TABLE_DST_INTERLEAVED
+        p.sample_block, p.table_order = 16, capi.TABLE_DST_INTERLEAVED
     for k, v in over.items():
         if not hasattr(p, k):
             raise AttributeError(k)
