@@ -658,16 +658,21 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     // slack32 / fire32 / vis32 are the per-pass 32-bit forms of the snapshot, lastFired and lastVisited that the line
     // kernel works on (traversal.cu:k_traverse_line32, k_prepare32, k_fold32): 12 bytes per neuron = 60 MB at 5M neurons,
     // the size of the persisting-L2 set-aside. The 64-bit arrays serve every other kernel, the read-out and the ABI.
+    // fire32 / vis32 exist for the OWNED neurons only (a sharded rank touches nothing else) and are indexed by global id
+    // through pointers offset by -lo: the persisting set-aside is then exactly what the rank touches — 4 N + 8 N/G bytes.
+    // (Measured at G = 2 with full-size arrays: the 60 MB set-aside, a third of it never touched, made the pass SLOWER
+    // than no set-aside at all, 0.84 vs 0.76 ms: profiles/r2_notes.md §5.)
     const u64 npad = (h->npad + 31) & ~31ull;
+    const u64 spad = (h->slice + 31) & ~31ull;
     const bool snap = p.src_view == ABNN_SRC_SNAPSHOT;
-    const u64 words = snap ? 9 : 4;                          // in units of npad * 4 bytes
-    CUH(cudaMalloc(&h->d_ts, words * npad * sizeof(u32)));
-    CUH(cudaMemsetAsync(h->d_ts, 0, words * npad * sizeof(u32), h->st));                       // brain.cpp:62-64
+    const u64 words = snap ? 7 * npad + 2 * spad : 4 * npad;   // in units of 4 bytes
+    CUH(cudaMalloc(&h->d_ts, words * sizeof(u32)));
+    CUH(cudaMemsetAsync(h->d_ts, 0, words * sizeof(u32), h->st));                               // brain.cpp:62-64
     if (snap) {
         h->d.slack = reinterpret_cast<u32*>(h->d_ts);
-        h->d.fire32 = reinterpret_cast<int*>(h->d.slack + npad);
-        h->d.vis32 = h->d.slack + 2 * npad;
-        h->d.visited = h->d_ts + 3 * npad / 2;
+        h->d.fire32 = reinterpret_cast<int*>(h->d.slack + npad) - h->lo;
+        h->d.vis32 = h->d.slack + npad + spad - h->lo;
+        h->d.visited = reinterpret_cast<u64*>(h->d.slack + npad + 2 * spad);
         h->d.live = h->d.visited + npad;
         h->d.view = h->d.live + npad;
     } else {
@@ -712,9 +717,9 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     if (p.l2_persist && max_persist > 0 && max_window > 0) {
         const int n_arr = tune_env("ABNN_L2_ARRAYS") ? atoi(tune_env("ABNN_L2_ARRAYS")) : 3;
         const bool miss_normal = tune_env("ABNN_L2_MISS") && atoi(tune_env("ABNN_L2_MISS")) == 1;
-        // default: slack32 + fire32 + vis32 (60 MB at 5M neurons) / LIVE view: lastFired + lastVisited
-        const u64 hot_words = snap ? (u64)std::max(1, std::min(n_arr, 9)) : (n_arr <= 1 ? 2 : 4);
-        size_t hot = (size_t)hot_words * npad * sizeof(u32);
+        // default: slack32 + the owned fire32 / vis32 (60 MB at 5M neurons on one GPU) / LIVE view: lastFired + lastVisited
+        size_t hot = snap ? (size_t)(npad + (n_arr >= 2 ? spad : 0) + (n_arr >= 3 ? spad : 0)) * sizeof(u32)
+                          : (size_t)(n_arr <= 1 ? 2 : 4) * npad * sizeof(u32);
         size_t want = std::min<size_t>(hot, (size_t)max_persist);
         if (tune_env("ABNN_L2_CARVE_MAX")) want = (size_t)max_persist;
         { size_t cur = 0; if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur > want) want = cur; }

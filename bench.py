@@ -547,12 +547,15 @@ def main():
         quiet_mean = float(q.item())
         t = torch.tensor([ms_total, e2e_s, float(np.mean(trav_ms)), float(np.mean(pass_ms)), struct_mean], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"traverse_ms": float(np.mean(trav_ms)), "gated_fraction": gated / max(1, evs), "events_per_pass": evs / max(1, min(K, 10))})
         cnt = torch.tensor([gated, fired, evs, n_after], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         ms_total, e2e_s, trav_mean, pass_mean, struct_mean = (float(x) for x in t.tolist())
         gated, fired, evs, n_after = (float(x) for x in cnt.tolist())
     else:
         trav_mean, pass_mean = float(np.mean(trav_ms)), float(np.mean(pass_ms))
+        per_rank = None
 
     parity = None
     if world > 1 and not args.skip_variants and not args.structural:
@@ -583,7 +586,7 @@ def main():
                                       "note": "same table, no neuron inside the pre-spike window (B_alg = 16 B/event)"},
             # where a step goes (device time, max over ranks): traversal kernel | + word build, end-of-pass, fold, exchange
             # | + inject, teacher, read-out and launch gaps = ms_per_step
-            "step_breakdown_ms": {"traverse": trav_mean, "pass_with_exchange": pass_mean, "step": ms_step},
+            "step_breakdown_ms": {"traverse": trav_mean, "pass_with_exchange": pass_mean, "step": ms_step, "per_rank": per_rank},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind,
                          "kernel": "k_traverse_line32" if line32 else ("k_traverse_line" if args.block == 8 else "k_traverse_parallel"),

@@ -172,14 +172,22 @@ typedef struct abnn_params {
     int32_t  device;               /* CUDA device ordinal; -1 = current device                  */
     uint32_t rank;                 /* 0 .. world_size-1                                         */
     uint32_t world_size;           /* 1 = single GPU                                            */
-    uint32_t l2_persist;           /* 1: pin the timestamp arrays in L2 with an access-policy window */
+    uint32_t l2_persist;           /* 1: keep the per-neuron 32-bit arrays resident in L2: raises the DEVICE-wide
+                                      cudaLimitPersistingL2CacheSize to what they need (never lowers it) and attaches an
+                                      access-policy window to the handle's stream; 0: no device-wide state is touched */
 
     /* PHILOX sampler granularity: events are drawn in groups of sample_block consecutive events that
      * process sample_block consecutive table records starting at a Philox-chosen, block-aligned
-     * position: edge(i) = B*mulhi64(philox(seed, i - i%B).xy, ceil(n/B)) + i%B  (skipped if >= n).
-     * 1 = every event draws its own edge (README.md:77). 8 = one 128-byte HBM line per draw (B200's
-     * DRAM fetch granularity: a random 16-byte gather costs a whole line, profiles/r1_notes.md §1).
-     * Power of two, <= 32. Every edge is still sampled with equal probability. */
+     * position: edge(i) = B*mulhi64(q.xy, ceil(n/B)) + i%B  (skipped if >= n), q = philox(seed, i - i%B): ONE Philox
+     * call per group; event k = i%B of the group takes its release draw from fmix32(q.z + k*0x9E3779B9) and its
+     * synaptogenesis trial from fmix32(q.w + k*0x85EBCA6B) (fmix32 = MurmurHash3's 32-bit finaliser; B = 1: q.z, q.w).
+     * 1 = every event draws its own edge (README.md:77). 8 = one 128-byte HBM line per draw (B200's DRAM fetch
+     * granularity: a random 16-byte gather costs a whole line, profiles/r1_notes.md §1). 16 = 256 bytes per draw, the
+     * size at which random HBM3e reads reach the copy bandwidth (profiles/r2_notes.md §1).
+     * Power of two, <= 32. Every edge is still sampled with equal probability, but with sample_block > 1 the events of a
+     * group arrive together: over a DST_SORTED table that is a burst on ONE neuron (fire rate 2-3 % below iid sampling),
+     * over a DST_INTERLEAVED table the group's events hit different neurons and the statistics are those of the iid
+     * sampler (tests/test_gpu_equivalence.py). */
     uint32_t sample_block;
     uint32_t table_order;          /* abnn_table_order                                          */
     uint32_t prune_in_place;       /* 0: pruning compacts into a second table when the device has memory for one (count +
@@ -234,7 +242,11 @@ void abnn_destroy(abnn_handle* h);                               /* Brain::relea
 int  abnn_get_info(abnn_handle* h, abnn_info* out);              /* getters brain.h:48-52      */
 
 /* ---- multi-GPU plumbing (new; the reference is single-device). One NCCL communicator per handle.
- * id is the 128-byte ncclUniqueId made by rank 0 and distributed by the host (any transport).   */
+ * id is the 128-byte ncclUniqueId made by rank 0 and distributed by the host (any transport).
+ * GPU-count invariance: the partition (abnn_partition), abnn_upload_synapses of one global table and the snapshot rule
+ * for lastFired[src] do not depend on world_size; the RESULTS of a run do — rank is part of the Philox counter, ticks
+ * are clock + i*world_size + rank, and ABNN_GRAPH_ER_BETA draws each rank's edges over its own neuron slice. A W-rank
+ * run is reproducible for a given (seed, W) and is checked against the W-shard oracle.            */
 int abnn_comm_unique_id(void* id128);
 int abnn_comm_init(abnn_handle* h, const void* id128);
 
@@ -244,14 +256,19 @@ int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed);
 int abnn_upload_synapses(abnn_handle* h, const abnn_synapse* syn, uint64_t n);
 /* This rank's live records, in table order. *n_out = count; fails with ABNN_ERR_CAPACITY if cap is short. */
 int abnn_download_synapses(abnn_handle* h, abnn_synapse* out, uint64_t cap, uint64_t* n_out);
-/* .bnn v1: u32 N_SYN, u32 N_NRN, N_SYN x 16-byte records, no padding (brain.cpp:161-167). */
+/* .bnn v1: u32 N_SYN, u32 N_NRN, N_SYN x 16-byte records, no padding (brain.cpp:161-167). save writes the LIVE record
+ * count; load wants N_NRN equal to the handle's and N_SYN <= its capacity (ABNN_ERR_SHAPE otherwise, where the reference
+ * throws: brain.cpp:174) and the whole table present in the file before it touches the device table. */
 int abnn_save_bnn(abnn_handle* h, const char* path);
-int abnn_load_bnn(abnn_handle* h, const char* path);             /* ABNN_ERR_SHAPE on mismatch (brain.cpp:174) */
+int abnn_load_bnn(abnn_handle* h, const char* path);
 
 /* .bnn v2 (new; README.md:237-241 lists what v1 lacks): everything needed to resume EXACTLY where the run
  * stopped — this rank's records, lastFired / lastVisited / snapshot, clock, pass and event counters,
  * reward, r-bar, read-out filter state, staged growth candidates. Header "BNN2", shape-checked like v1.
- * One file per rank. Both synchronise. */
+ * One file per rank. Both synchronise. load refuses (ABNN_ERR_SHAPE) a file written under other semantics — sampler,
+ * release_rng, clock_mode, src_view, rbar_mode, sample_block, table_order, seed, window_pre, refractory, teacher_gap,
+ * budget, track_visits, shape — while exec_mode, learning rates and placement may differ; the file is checked for
+ * completeness before any device state is overwritten. */
 int abnn_save_state(abnn_handle* h, const char* path);
 int abnn_load_state(abnn_handle* h, const char* path);
 
@@ -271,9 +288,10 @@ int abnn_sync(abnn_handle* h);                                           /* wait
 /* One whole engine pass without a host round trip — BrainEngine::run_one_pass (brain-engine.cpp:108-190):
  * stage the stimulus frame, inject_inputs(in, hz), teacher forcing (expected, teacher_rate), `events`
  * traversal events, timestamp exchange, read-out step with loss/reward. Equivalent to abnn_inject_inputs +
- * abnn_teacher_force + abnn_run_pass(NULL) + abnn_readout_step; in PARALLEL execution on a single-GPU
- * handle the device work is recorded into a CUDA graph on the second call and replayed while events /
- * table size stay the same (sharded handles enqueue the same sequence eagerly).
+ * abnn_teacher_force + abnn_run_pass(NULL) + abnn_readout_step; the device work is recorded into a CUDA graph on
+ * the second call and replayed while events / table size stay the same: PARALLEL and EXACT execution on single-GPU
+ * handles, PARALLEL on sharded handles with exchange = ABNN_EXCHANGE_PEER (with the NCCL exchange sharded handles
+ * enqueue the same sequence eagerly).
  * Asynchronous when rates == NULL; otherwise writes the n_output filtered rates and synchronises. */
 int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, float hz, float teacher_rate,
                      uint64_t events, float* rates);
@@ -291,8 +309,10 @@ int abnn_readout_filtered(abnn_handle* h, const float* expected, float* rates, u
 int abnn_readout_step(abnn_handle* h, const float* expected, uint32_t n);
 int abnn_get_loss(abnn_handle* h, double* last_loss, uint64_t* windows_done);   /* synchronises */
 
-/* ---- structural plasticity (README.md:120-127): stable prune-compaction, then ordered append - */
-int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* stats);   /* synchronises */
+/* ---- structural plasticity (README.md:120-127): stable prune-compaction, then ordered append. Collective on sharded
+ * handles (growth candidates are allgathered): a growth-buffer overflow on ANY rank makes every rank return
+ * ABNN_ERR_CAPACITY together (the candidates of that interval are dropped). Synchronises. */
+int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* stats);
 
 /* ---- raw state access: last_fired_buffer()/clock_buffer() (brain.h:54-58). All synchronise. - */
 int abnn_download_timestamps(abnn_handle* h, uint64_t* last_fired, uint64_t* last_visited); /* n_neuron each; NULL to skip */

@@ -471,6 +471,17 @@ def test_bnn_roundtrip_and_shape_error(tmp_path):
         with pytest.raises(capi.AbnnError) as e:
             b.load(path)
         assert e.value.status == capi.ERR_SHAPE                                                  # brain.cpp:174
+    # a pruned table (live count below n_syn) written by abnn_save_bnn loads back
+    pr = O.default_params(capi.PROFILE_NORTH_STAR, **dict(over, w_prune=0.15))
+    with Brain(pr) as b:
+        b.build_random_graph(1)
+        st = b.prune_and_grow()
+        assert 0 < st.n_after < 5000
+        kept = b.download_synapses()
+        b.save(path)
+    with Brain(pr) as b:
+        b.load(path)
+        assert b.download_synapses().tobytes() == kept.tobytes()
 
 
 def test_bnn_v2_exact_resume(tmp_path):
@@ -511,6 +522,26 @@ def test_bnn_v2_exact_resume(tmp_path):
         with pytest.raises(capi.AbnnError) as e:
             other.load_state(path)
         assert e.value.status == capi.ERR_SHAPE
+    # a state file means what the fields it was written under say: another table order / sampler / seed / window is refused
+    # (a GIVEN-order table in a sorted handle would break the sorted insertion), while the execution mode may change
+    for bad in (dict(table_order=capi.TABLE_AS_GIVEN), dict(sample_block=1), dict(seed=43), dict(window_pre=400_001)):
+        with Brain(O.default_params(capi.PROFILE_NORTH_STAR, **dict(over, **bad))) as other:
+            with pytest.raises(capi.AbnnError) as e:
+                other.load_state(path)
+            assert e.value.status == capi.ERR_SHAPE, bad
+    with Brain(O.default_params(capi.PROFILE_NORTH_STAR, **dict(over, exec_mode=capi.EXEC_SERIAL))) as other:
+        other.load_state(path)                                       # same semantics, other execution mode: accepted
+        assert other.info().n_syn_local > 0
+    short = str(tmp_path / "short.bnn2")
+    raw = open(path, "rb").read()
+    open(short, "wb").write(raw[:len(raw) - 1000])
+    with Brain(O.default_params(capi.PROFILE_NORTH_STAR, **over)) as other:
+        other.build_random_graph(1)
+        before = other.download_synapses().tobytes()
+        with pytest.raises(capi.AbnnError) as e:
+            other.load_state(short)
+        assert e.value.status == capi.ERR_IO
+        assert other.download_synapses().tobytes() == before          # a truncated file leaves the handle untouched
 
 
 # ---- structural plasticity ---------------------------------------------------------------------------
