@@ -55,6 +55,7 @@ class Params(C.Structure):
         ("device", C.c_int32), ("rank", C.c_uint32), ("world_size", C.c_uint32),
         ("l2_persist", C.c_uint32),
         ("sample_block", C.c_uint32), ("table_order", C.c_uint32), ("prune_in_place", C.c_uint32), ("exchange", C.c_uint32),
+        ("compact_every", C.c_uint32), ("reserved_", C.c_uint32),
     ]
 
     def copy(self) -> "Params":

@@ -43,12 +43,18 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 constexpr int    RING = 16;             // pinned host staging slots for small per-pass vectors
 constexpr u64    UPLOAD_CHUNK = 8ull << 20;   // records per upload chunk (128 MB)
 constexpr u32    GROW_CAP_DEFAULT = 1u << 20;
+constexpr u32    PRUNE_CAP_DEFAULT = 1u << 22;   // staged prune candidates between two structural steps (compact_every > 1)
 
 u32 next_pow2(u32 v) { u32 p = 1; while (p < v) p <<= 1; return p; }
 
 __global__ void k_set_reward(DevScalars* sc, float r) { sc->reward = r; }
 __global__ void k_set_clock(DevScalars* sc, u64 c) { sc->clock = c; }
 __global__ void k_reset_grow(DevScalars* sc) { sc->grow_count = 0; sc->grow_overflow = 0; }
+// bookkeeping of the structural steps (compact_every > 1): step counter, ordered region, dead records, staged candidates
+__global__ void k_set_struct(DevScalars* sc, u64 steps, u64 n_sorted, u64 n_dead)
+{
+    sc->struct_steps = steps; sc->n_sorted = n_sorted; sc->n_dead = n_dead; sc->prune_count = 0; sc->prune_overflow = 0;
+}
 __global__ void k_pad_grow(GrowCand* c, u32 from, u32 to)
 {
     const u32 i = from + blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,6 +83,7 @@ struct abnn_handle {
     u64* d_ts = nullptr;
     DevPtrs d{};
     u32 grow_cap = 0, grow_buf = 0;
+    u64 struct_steps = 0, n_sorted = 0, n_dead = 0;   // host mirror of DevScalars (compact_every > 1)
     GrowCand* d_grow_all = nullptr; u32 grow_all_buf = 0;
     float* d_vec = nullptr;               // RING slots of max(n_input,n_output) floats
     float* h_vec = nullptr;               // pinned mirror
@@ -185,6 +192,8 @@ KParams make_kparams(const abnn_handle* h, u64 events)
     k.base_scale = p.base_scale; k.a_ltp = p.a_ltp; k.a_ltd = p.a_ltd; k.w_min = p.w_min; k.w_max = p.w_max;
     k.eta_home = p.eta_home; k.target_rate_hz = p.target_rate_hz; k.home_tick_hz = p.home_tick_hz;
     k.eta_reward = p.eta_reward; k.alpha_rbar = p.alpha_rbar; k.p_new = p.p_new;
+    k.lazy_prune = (p.compact_every > 1 && p.w_prune > 0.f && h->d.prune_list) ? 1u : 0u;
+    k.prune_cap = PRUNE_CAP_DEFAULT; k.w_prune = p.w_prune;
     return k;
 }
 
@@ -383,6 +392,15 @@ int append_chunk(abnn_handle* h, const abnn_synapse* host, u64 n)
     return 0;
 }
 
+// A new table (upload / init / load): the structural-step bookkeeping starts over — the whole table is the ordered region.
+int reset_structural(abnn_handle* h)
+{
+    h->struct_steps = 0; h->n_sorted = h->n_local; h->n_dead = 0;
+    k_set_struct<<<1, 1, 0, h->st>>>(h->d.sc, 0, h->n_local, 0);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // ABNN_TABLE_DST_SORTED: keep the rank's table stably sorted by destination neuron (include/abnn.h).
 // Scratch (a second table + two key arrays) is allocated for the duration of the sort only.
 int sort_table(abnn_handle* h)
@@ -417,13 +435,16 @@ int sort_table(abnn_handle* h)
 // are cached in the handle). With kept_out != null the
 // pruning (w < w_prune) happens in the same pass over the table (launch_prune_merge_sorted) and *kept_out receives the
 // number of existing records that survived.
-int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nullptr)
+// With list == null the m new records are already in h->mg_new (the filtered tail of a periodic rebuild) and n_ordered is
+// the size of the ordered region they are merged into.
+int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nullptr, u64 n_ordered = ~0ull)
 {
-    const u64 n = h->n_local;
+    const u64 n = n_ordered == ~0ull ? h->n_local : n_ordered;
     const u32 span = (u32)(h->hi - h->lo);
     // scratch for the new records is cached in the handle (cudaMalloc / cudaFree next to a 16 GB table cost more
     // than the merge itself)
     if (m > h->mg_cap) {
+        if (!list) return fail(ABNN_ERR_INVALID, "merge_grown: ready records need the scratch sized beforehand");
         cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp);
         h->mg_new = nullptr; h->mg_keys = nullptr; h->mg_tmp = nullptr; h->mg_cap = 0;
         const u32 cap_m = next_pow2(m);
@@ -447,7 +468,7 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nul
     if (!out) CU(cudaMalloc(&out, h->cap * sizeof(abnn_synapse)));
     abnn_synapse *nw = h->mg_new, *nw_alt = h->mg_new + h->mg_cap;
     cudaError_t e = cudaMemsetAsync(h->mg_cnt, 0, ((size_t)span + 1) * sizeof(u32), h->st);
-    if (e == cudaSuccess) e = launch_grow_append(list, m, nw, 0, h->p.w_init, h->st);
+    if (e == cudaSuccess && list) e = launch_grow_append(list, m, nw, 0, h->p.w_init, h->st);
     bool in_alt = false;
     int nb = 1; while ((1ull << nb) < h->N) ++nb;
     if (e == cudaSuccess) e = launch_sort_by_dst(nw, nw_alt, h->mg_keys, h->mg_keys + h->mg_cap, m, nb, h->mg_tmp, h->mg_tmp_bytes, &in_alt, h->st);
@@ -588,6 +609,8 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
         return fail(ABNN_ERR_INVALID, "unknown mode value");
     if (p.table_order > ABNN_TABLE_DST_INTERLEAVED) return fail(ABNN_ERR_INVALID, "unknown table_order");
     if (p.exchange > ABNN_EXCHANGE_PEER || p.prune_in_place > 1) return fail(ABNN_ERR_INVALID, "unknown exchange / prune_in_place value");
+    if (p.compact_every > 1 && p.w_prune > 0.f && p.p_new > 0.f && p.w_init < p.w_prune)
+        return fail(ABNN_ERR_INVALID, "compact_every > 1 needs w_init >= w_prune (a grown synapse below the pruning threshold would never be staged)");
     if (p.sample_block > 32 || (p.sample_block & (p.sample_block - 1)))
         return fail(ABNN_ERR_INVALID, "sample_block must be a power of two <= 32 (0 = 1)");
     if (!p.n_output || p.fir_size == 0 || p.fir_size > ABNN_MAX_FIR) return fail(ABNN_ERR_INVALID, "bad n_output / fir_size");
@@ -690,6 +713,7 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     h->grow_cap = GROW_CAP_DEFAULT;
     h->grow_buf = next_pow2(h->grow_cap);
     if (p.p_new > 0.f) CUH(cudaMalloc(&h->d.grow, (size_t)h->grow_buf * sizeof(GrowCand)));
+    if (p.compact_every > 1 && p.w_prune > 0.f) CUH(cudaMalloc(&h->d.prune_list, (size_t)PRUNE_CAP_DEFAULT * sizeof(u64)));
     h->vec_len = std::max(p.n_input, p.n_output);
     CUH(cudaMalloc(&h->d_vec, (size_t)RING * h->vec_len * sizeof(float)));
     CUH(cudaMallocHost(&h->h_vec, (size_t)RING * h->vec_len * sizeof(float)));
@@ -756,6 +780,7 @@ void abnn_destroy(abnn_handle* h)
     if (h->comm) ncclCommDestroy(h->comm);
     cudaFree(h->d_syn); cudaFree(h->d_spare); cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp); cudaFree(h->mg_cnt);
     cudaFree(h->mg_pruned); cudaFree(h->mg_scan); cudaFree(h->d_ts); cudaFree(h->d.sc); cudaFree(h->d.grow); cudaFree(h->d_grow_all);
+    cudaFree(h->d.prune_list);
     cudaFree(h->d_vec); cudaFreeHost(h->h_vec);
     cudaFree(h->rs.rate); cudaFree(h->rs.iir); cudaFree(h->rs.fir); cudaFree(h->rs.smooth); cudaFree(h->rs.spikes);
     cudaFree(h->d_stats); cudaFreeHost(h->h_pin); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -822,6 +847,7 @@ int abnn_upload_synapses(abnn_handle* h, const abnn_synapse* syn, uint64_t n)
     h->n_local = 0;
     RET(append_chunk(h, syn, n));
     RET(sort_table(h));
+    RET(reset_structural(h));
     h->counts_dirty = true;
     if (h->p.world_size == 1) h->n_local_all.assign(1, h->n_local);
     return 0;
@@ -850,6 +876,7 @@ int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed)
         CU(launch_init_er_beta(h->d_syn, g0, g1 - g0, seed, h->N, h->lo, h->hi, h->sm_count, h->st));
         h->n_local = g1 - g0;
         RET(sort_table(h));
+        RET(reset_structural(h));
         for (u32 k = 0; k < p.world_size; ++k)
             h->n_local_all[k] = (u64)((unsigned __int128)p.n_syn * (k + 1) / p.world_size) -
                                 (u64)((unsigned __int128)p.n_syn * k / p.world_size);
@@ -885,6 +912,7 @@ int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed)
             if (fill == chunk || idx == p.n_syn) { RET(append_chunk(h, buf.data(), fill)); fill = 0; }
         }
         RET(sort_table(h));
+        RET(reset_structural(h));
         h->counts_dirty = true;
         if (p.world_size == 1) h->n_local_all.assign(1, h->n_local);
         return 0;
@@ -950,6 +978,7 @@ int abnn_load_bnn(abnn_handle* h, const char* path)
     std::fclose(f);
     h->n_local = n; h->n_local_all.assign(1, n); h->counts_dirty = false;
     RET(sort_table(h));
+    RET(reset_structural(h));
     return 0;
 }
 
@@ -961,6 +990,7 @@ struct Bnn2Header {
     uint64_t n_local, n_neuron, n_syn_global;
     uint32_t rank, world, n_output, fir_size;
     uint32_t grow_count, snapshot;
+    uint32_t prune_count, pad_;
 };
 bool put(FILE* f, const void* p, size_t n) { return n == 0 || std::fwrite(p, 1, n, f) == n; }
 bool get(FILE* f, void* p, size_t n) { return n == 0 || std::fread(p, 1, n, f) == n; }
@@ -1003,6 +1033,7 @@ int abnn_save_state(abnn_handle* h, const char* path)
     for (u64 v : h->n_local_all) hd.n_syn_global += v;
     hd.rank = h->p.rank; hd.world = h->p.world_size; hd.n_output = h->p.n_output; hd.fir_size = h->p.fir_size;
     hd.grow_count = h->d.grow ? std::min(sc.grow_count, h->grow_cap) : 0;
+    hd.prune_count = h->d.prune_list ? std::min(sc.prune_count, PRUNE_CAP_DEFAULT) : 0;
     hd.snapshot = h->d.view != h->d.live;
     std::vector<char> buf(64u << 20);
     int rc = 0;
@@ -1018,6 +1049,7 @@ int abnn_save_state(abnn_handle* h, const char* path)
     if (!rc) rc = dev_to_file(h, f, h->d.visited, h->N * sizeof(u64), buf);
     if (!rc && hd.snapshot) rc = dev_to_file(h, f, h->d.view, h->N * sizeof(u64), buf);
     if (!rc && hd.grow_count) rc = dev_to_file(h, f, h->d.grow, (size_t)hd.grow_count * sizeof(GrowCand), buf);
+    if (!rc && hd.prune_count) rc = dev_to_file(h, f, h->d.prune_list, (size_t)hd.prune_count * sizeof(u64), buf);
     if (!rc) rc = dev_to_file(h, f, h->d_syn, h->n_local * sizeof(abnn_synapse), buf);
     if (std::fclose(f) != 0 && !rc) rc = fail(ABNN_ERR_IO, std::string("short write: ") + path);
     return rc;
@@ -1040,6 +1072,7 @@ int abnn_load_state(abnn_handle* h, const char* path)
         rc = fail(ABNN_ERR_SHAPE, ".bnn v2 header does not match the handle (neurons / rank / world / read-out / src view)");
     else if (hd.n_local > h->cap) rc = fail(ABNN_ERR_CAPACITY, "synapse table capacity exceeded");
     else if (hd.grow_count && (!h->d.grow || hd.grow_count > h->grow_buf)) rc = fail(ABNN_ERR_SHAPE, ".bnn v2 holds staged growth but the handle has p_new = 0");
+    else if (hd.prune_count && (!h->d.prune_list || hd.prune_count > PRUNE_CAP_DEFAULT)) rc = fail(ABNN_ERR_SHAPE, ".bnn v2 holds staged prune candidates but the handle has compact_every <= 1");
     std::vector<u64> counts(h->p.world_size);
     if (!rc && !(get(f, &saved, sizeof saved) && get(f, &sc, sizeof sc) && get(f, counts.data(), counts.size() * sizeof(u64))))
         rc = fail(ABNN_ERR_IO, "short read");
@@ -1053,14 +1086,14 @@ int abnn_load_state(abnn_handle* h, const char* path)
             a.rbar_mode != b.rbar_mode || a.sample_block != b.sample_block || a.table_order != b.table_order || a.seed != b.seed ||
             a.window_pre != b.window_pre || a.refractory != b.refractory || a.teacher_gap != b.teacher_gap ||
             a.max_spikes_per_pass != b.max_spikes_per_pass || a.track_visits != b.track_visits || a.n_input != b.n_input ||
-            a.n_hidden != b.n_hidden)
+            a.n_hidden != b.n_hidden || (a.compact_every > 1 ? a.compact_every : 1) != (b.compact_every > 1 ? b.compact_every : 1))
             rc = fail(ABNN_ERR_SHAPE, ".bnn v2 was written under different semantics (sampler / sample_block / table_order / clock / src view / "
                                       "r-bar mode / seed / window / refractory / budget / visits / shape differ from the handle's)");
     }
     if (!rc) {   // everything the rest of the file must hold, checked before any device state is overwritten
         const size_t no_ = h->p.n_output;
         const u64 need = (u64)(3 + h->p.fir_size) * no_ * sizeof(float) + (u64)(hd.snapshot ? 3 : 2) * h->N * sizeof(u64) +
-                         (u64)hd.grow_count * sizeof(GrowCand) + hd.n_local * sizeof(abnn_synapse);
+                         (u64)hd.grow_count * sizeof(GrowCand) + (u64)hd.prune_count * sizeof(u64) + hd.n_local * sizeof(abnn_synapse);
         const long at = std::ftell(f);
         std::fseek(f, 0, SEEK_END);
         const long end = std::ftell(f);
@@ -1077,12 +1110,14 @@ int abnn_load_state(abnn_handle* h, const char* path)
     if (!rc) rc = file_to_dev(h, f, h->d.visited, h->N * sizeof(u64), buf);
     if (!rc && hd.snapshot) rc = file_to_dev(h, f, h->d.view, h->N * sizeof(u64), buf);
     if (!rc && hd.grow_count) rc = file_to_dev(h, f, h->d.grow, (size_t)hd.grow_count * sizeof(GrowCand), buf);
+    if (!rc && hd.prune_count) rc = file_to_dev(h, f, h->d.prune_list, (size_t)hd.prune_count * sizeof(u64), buf);
     if (!rc) rc = file_to_dev(h, f, h->d_syn, hd.n_local * sizeof(abnn_synapse), buf);
     std::fclose(f);
     if (rc) return rc;
     if (cudaMemcpyAsync(h->d.sc, &sc, sizeof sc, cudaMemcpyHostToDevice, h->st) != cudaSuccess || cudaStreamSynchronize(h->st) != cudaSuccess)
         return fail(ABNN_ERR_CUDA, "device write failed during load");
     h->n_local = hd.n_local; h->n_local_all = counts; h->counts_dirty = false;
+    h->struct_steps = sc.struct_steps; h->n_sorted = sc.n_sorted; h->n_dead = sc.n_dead;
     h->slack_ready = false; h->fire_ready = false; h->view_stale = false;
     if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }
     return 0;
@@ -1103,6 +1138,7 @@ const Field kFields[] = {
     FLD(rate_alpha, F_F32), FLD(peak_decay, F_F32), FLD(peak_init, F_F32), FLD(use_fir, F_U32), FLD(fir_size, F_U32),
     FLD(reward_window, F_U32), FLD(filter_tau, F_F64), FLD(dt_sec, F_F64), FLD(loss0, F_F64), FLD(device, F_I32),
     FLD(l2_persist, F_U32), FLD(sample_block, F_U32), FLD(table_order, F_U32), FLD(prune_in_place, F_U32), FLD(exchange, F_U32),
+    FLD(compact_every, F_U32),
 };
 #undef FLD
 std::string trim(const std::string& s)
@@ -1457,11 +1493,11 @@ int abnn_get_loss(abnn_handle* h, double* last_loss, uint64_t* windows_done)
 namespace {
 // Growth candidates staged since the last structural step, from every rank, sorted by the tick ordinal of the firing
 // event; *owned = how many of them target this rank's neurons (they sort first). Collective when world_size > 1.
-int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out)
+int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out, bool other_overflow = false)
 {
     *list_out = h->d.grow; *owned_out = 0;
     DevScalars sc; RET(read_scalars(h, &sc));
-    bool overflow = sc.grow_overflow != 0;
+    bool overflow = sc.grow_overflow != 0 || other_overflow;      // (the prune staging buffer of compact_every > 1 shares the agreement)
     u32 n = std::min(sc.grow_count, h->grow_cap);
     GrowCand* list = h->d.grow;
     u32 total = n;
@@ -1479,8 +1515,9 @@ int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out)
     }
     if (overflow) {                                          // the same status on every rank; the staged candidates are dropped
         k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
+        k_set_struct<<<1, 1, 0, h->st>>>(h->d.sc, h->struct_steps, h->n_sorted, h->n_dead);    // drops the staged prune candidates too
         CU(cudaStreamSynchronize(h->st));
-        return fail(ABNN_ERR_CAPACITY, "growth staging buffer overflowed on a rank (candidates of this interval are dropped); call abnn_prune_and_grow more often");
+        return fail(ABNN_ERR_CAPACITY, "growth / prune staging buffer overflowed on a rank (candidates of this interval are dropped); call abnn_prune_and_grow more often");
     }
     if (h->p.world_size > 1) {
         u32 maxc = 0;
@@ -1515,6 +1552,113 @@ int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out)
 }
 }  // namespace
 
+// Stable prune-compaction of the whole table: into the spare table (count pass + scatter pass, no chained scan) when
+// there is memory for one, else in place (k_compact). Dead records (compact_every > 1) carry weights below w_prune and go
+// with the rest. *kept = surviving records; h->n_local is updated.
+static int prune_compact(abnn_handle* h, u64* kept_out)
+{
+    const bool in_place_only = h->p.prune_in_place != 0;
+    const bool two_tables = 2 * h->cap * sizeof(abnn_synapse) <= h->mem_total / 2;
+    abnn_synapse* spare = nullptr;
+    if (!in_place_only && (h->d_spare || two_tables)) {
+        spare = h->d_spare; h->d_spare = nullptr;
+        if (!spare && cudaMalloc(&spare, h->cap * sizeof(abnn_synapse)) != cudaSuccess) { cudaGetLastError(); spare = nullptr; }
+    }
+    CompactArgs a{};
+    a.in = h->d_syn; a.out = spare ? spare : h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
+    a.out_cap = h->cap;
+    u64 kept = 0;
+    cudaError_t e = cudaSuccess;
+    int rc = ensure_scratch(h, spare ? compact2_scratch_bytes(h->cap) : compact_scratch_bytes(h->cap));   // by capacity: never regrown
+    if (!rc) {
+        e = spare ? launch_compact_two_pass(a, h->d_scratch, h->d_total, h->st) : launch_compact(a, h->d_scratch, h->d_total, h->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    }
+    if (rc || e != cudaSuccess) {
+        if (spare) h->d_spare = spare;               // the table itself is untouched when the copy went elsewhere
+        if (rc) return rc;
+        return fail(ABNN_ERR_CUDA, std::string("prune: ") + cudaGetErrorString(e));
+    }
+    if (spare) {                                     // the old table becomes the spare of the next structural step
+        h->d_spare = h->d_syn;
+        h->d_syn = spare; h->d.syn = spare;
+        if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old pointer
+    }
+    h->n_local = kept;
+    *kept_out = kept;
+    return 0;
+}
+
+// compact_every > 1 (README.md:122-124 "remove, compact periodically"). Every step: the staged prune candidates that are
+// still below w_prune die in place, the owned growth candidates are appended behind the table in tick order — the step
+// touches what changed, not the table. Steps 0, K, 2K, ... additionally rebuild the table: dead and pruned records leave
+// (the whole table is swept then, so candidates are not needed), the tail is merged into the ordered region in the stable
+// order the eager mode keeps (DST_SORTED: sorted insertion behind the existing records of each destination; INTERLEAVED:
+// re-derived; AS_GIVEN: the tail already is where it belongs).
+static int lazy_structural_step(abnn_handle* h, abnn_structural_stats* s, GrowCand* list, u32 owned, const DevScalars& sc)
+{
+    const bool rebuild = h->struct_steps % h->p.compact_every == 0;
+    const bool prune = h->p.w_prune > 0.f;
+    // 1. pruned records die in place (not on a rebuild step: its sweep removes everything below w_prune)
+    u64 marked = 0;
+    if (prune && !rebuild) {
+        CU(launch_mark_dead(h->d.prune_list, std::min(sc.prune_count, PRUNE_CAP_DEFAULT), h->d_syn, h->p.w_prune, h->d_total + 2, h->st));
+        CU(cudaMemcpyAsync(&marked, h->d_total + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+    }
+    // 2. the grown synapses join the tail, in tick order, as many as fit
+    const u32 m = (u32)std::min<u64>(owned, h->cap - h->n_local);
+    if (m) CU(launch_grow_append(list, m, h->d_syn, h->n_local, h->p.w_init, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const u64 slots = h->n_local + m;                // table slots before any rebuild
+    h->n_local = slots;
+    s->appended = m; s->dropped = owned - m;
+    if (!rebuild) {
+        s->pruned = marked;
+        h->n_dead += marked;
+    } else {
+        const u64 alive_before = slots - h->n_dead;
+        const u64 tail = slots - h->n_sorted;
+        if (h->p.table_order == ABNN_TABLE_DST_SORTED && prune && tail && tail < (1ull << 31) && h->n_sorted) {
+            // the tail's survivors become the "new records" of the fused prune + sorted-insertion sweep of the ordered region
+            const u32 cap_m = next_pow2((u32)tail);
+            if (cap_m > h->mg_cap) {
+                cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp);
+                h->mg_new = nullptr; h->mg_keys = nullptr; h->mg_tmp = nullptr; h->mg_cap = 0;
+                h->mg_tmp_bytes = sort_by_dst_temp_bytes(cap_m);
+                CU(cudaMalloc(&h->mg_new, 2 * (size_t)cap_m * sizeof(abnn_synapse)));
+                CU(cudaMalloc(&h->mg_keys, 2 * (size_t)cap_m * sizeof(u32)));
+                CU(cudaMalloc(&h->mg_tmp, h->mg_tmp_bytes ? h->mg_tmp_bytes : 16));
+                h->mg_cap = cap_m;
+            }
+            CompactArgs a{};
+            a.in = h->d_syn + h->n_sorted; a.out = h->mg_new; a.n = tail; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune; a.out_cap = h->mg_cap;
+            RET(ensure_scratch(h, std::max(compact_scratch_bytes(h->cap), compact2_scratch_bytes(h->cap))));
+            CU(launch_compact(a, h->d_scratch, h->d_total, h->st));
+            u64 m2 = 0;
+            CU(cudaMemcpyAsync(&m2, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            u64 kept = 0;
+            if (m2) RET(merge_grown(h, nullptr, (u32)m2, &kept, h->n_sorted));       // sets n_local = kept + m2
+            else { h->n_local = h->n_sorted; RET(prune_compact(h, &kept)); }
+        } else {
+            u64 kept = slots;
+            if (prune) RET(prune_compact(h, &kept));
+            const bool resort = h->p.table_order == ABNN_TABLE_DST_INTERLEAVED ? (tail != 0 || kept != slots)
+                                                                                 : (h->p.table_order == ABNN_TABLE_DST_SORTED && tail != 0);
+            if (resort) RET(sort_table(h));
+        }
+        s->pruned = alive_before - h->n_local;
+        h->n_sorted = h->n_local;
+        h->n_dead = 0;
+    }
+    h->struct_steps += 1;
+    if (rebuild) h->n_sorted = h->n_local;
+    k_set_struct<<<1, 1, 0, h->st>>>(h->d.sc, h->struct_steps, h->n_sorted, h->n_dead);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
 {
     RET(use(h));
@@ -1523,50 +1667,32 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
     const bool prune = h->p.w_prune > 0.f && h->n_local, grow = h->p.p_new > 0.f;
     static const bool resort = tune_env("ABNN_GROW_RESORT") != nullptr;      // measurements: full radix re-sort instead of the merge
     static const bool no_fuse = tune_env("ABNN_NO_FUSED_PRUNE") != nullptr;  // measurements: prune and merge as two passes
+    const bool lazy = h->p.compact_every > 1;
+    DevScalars sc{};
+    if (lazy) RET(read_scalars(h, &sc));
     // growth candidates first (they do not depend on the table): their number decides how the table is rewritten
     GrowCand* list = nullptr;
     u32 owned = 0;
-    if (grow) RET(gather_growth(h, &list, &owned));
-    if (prune && owned && h->p.table_order == ABNN_TABLE_DST_SORTED && !resort && !no_fuse && owned <= h->cap - h->n_local) {
+    if (grow) RET(gather_growth(h, &list, &owned, lazy && sc.prune_overflow != 0));
+    else if (lazy && sc.prune_overflow) {
+        k_set_struct<<<1, 1, 0, h->st>>>(h->d.sc, h->struct_steps, h->n_sorted, h->n_dead);
+        return fail(ABNN_ERR_CAPACITY, "prune staging buffer overflowed; call abnn_prune_and_grow more often");
+    }
+    if (lazy) {
+        RET(lazy_structural_step(h, &s, list, owned, sc));
+    } else if (prune && owned && h->p.table_order == ABNN_TABLE_DST_SORTED && !resort && !no_fuse && owned <= h->cap - h->n_local) {
         // 1+2 fused: one pass over the table removes the pruned records and opens the slots of the new ones
         u64 kept = 0;
         RET(merge_grown(h, list, owned, &kept));
         s.pruned = s.n_before - kept;
         s.appended = owned;
     } else {
-        // 1. prune: stable compaction — into the spare table (count pass + scatter pass, no chained scan) when there is
-        //    memory for one, else in place (k_compact)
+        // 1. prune: stable compaction
         if (prune) {
-            const bool in_place_only = h->p.prune_in_place != 0;
-            const bool two_tables = 2 * h->cap * sizeof(abnn_synapse) <= h->mem_total / 2;
-            abnn_synapse* spare = nullptr;
-            if (!in_place_only && (h->d_spare || two_tables)) {
-                spare = h->d_spare; h->d_spare = nullptr;
-                if (!spare && cudaMalloc(&spare, h->cap * sizeof(abnn_synapse)) != cudaSuccess) { cudaGetLastError(); spare = nullptr; }
-            }
-            CompactArgs a{};
-            a.in = h->d_syn; a.out = spare ? spare : h->d_syn; a.n = h->n_local; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune;
-            a.out_cap = h->cap;
             u64 kept = 0;
-            cudaError_t e = cudaSuccess;
-            int rc = ensure_scratch(h, spare ? compact2_scratch_bytes(h->cap) : compact_scratch_bytes(h->cap));   // by capacity: never regrown
-            if (!rc) {
-                e = spare ? launch_compact_two_pass(a, h->d_scratch, h->d_total, h->st) : launch_compact(a, h->d_scratch, h->d_total, h->st);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, h->d_total, sizeof(u64), cudaMemcpyDeviceToHost, h->st);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
-            }
-            if (rc || e != cudaSuccess) {
-                if (spare) h->d_spare = spare;               // the table itself is untouched when the copy went elsewhere
-                if (rc) return rc;
-                return fail(ABNN_ERR_CUDA, std::string("prune: ") + cudaGetErrorString(e));
-            }
-            if (spare) {                                     // the old table becomes the spare of the next structural step
-                h->d_spare = h->d_syn;
-                h->d_syn = spare; h->d.syn = spare;
-                if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old pointer
-            }
-            s.pruned = h->n_local - kept;
-            h->n_local = kept;
+            const u64 before = h->n_local;
+            RET(prune_compact(h, &kept));
+            s.pruned = before - kept;
             if (s.pruned && h->p.table_order == ABNN_TABLE_DST_INTERLEAVED) RET(sort_table(h));   // the interleaved order is re-derived after every change
         }
         // 2. grow: candidates in event order, as many as fit
@@ -1588,6 +1714,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(h->st));
+    if (!lazy) { h->n_sorted = h->n_local; }
     s.n_after = h->n_local;
     h->counts_dirty = true;
     if (h->p.world_size == 1) h->n_local_all.assign(1, h->n_local);

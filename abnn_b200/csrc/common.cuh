@@ -133,6 +133,12 @@ struct DevScalars {
     double last_loss;
     // compaction scratch
     u64   compact_total;
+    // structural plasticity with periodic rebuilds (abnn_params.compact_every > 1)
+    u64   struct_steps;      // structural steps since the table was uploaded / initialised / loaded
+    u64   n_sorted;          // records of the ordered region (the rest of the table is the appended tail)
+    u64   n_dead;            // dead records waiting for the next rebuild
+    u32   prune_count;       // staged prune candidates (records written below w_prune since the last structural step)
+    u32   prune_overflow;
 };
 
 // Everything a traversal kernel needs, passed by value (constant bank).
@@ -156,6 +162,9 @@ struct KParams {
     float p_new;
     u32 use_slack;       // the line kernel reads DevPtrs::slack instead of the 64-bit snapshot
     u32 use_line32;      // k_traverse_line32 runs this pass (32-bit pass-relative timestamps)
+    u32 lazy_prune;      // compact_every > 1: a weight written below w_prune stages its record for the next structural step
+    u32 prune_cap;
+    float w_prune;
 };
 
 struct DevPtrs {
@@ -168,6 +177,19 @@ struct DevPtrs {
     u32* vis32;          // per-pass 32-bit form of lastVisited (k_traverse_line32), or null
     DevScalars* sc;
     GrowCand* grow;
+    u64* prune_list;     // staged prune candidates (table indices), or null
 };
+
+constexpr u32 DEAD_SRC = ABNN_DEAD_SRC;
+
+// A weight has just been written below w_prune: remember the record for the next structural step (compact_every > 1;
+// the step then never has to sweep the table to find what to prune).
+__device__ __forceinline__ void stage_prune(const KParams& kp, const DevPtrs& d, u64 edge, float w_new)
+{
+    if (!kp.lazy_prune || !(w_new < kp.w_prune)) return;
+    const u32 slot = atomicAdd(&d.sc->prune_count, 1u);
+    if (slot < kp.prune_cap) d.prune_list[slot] = edge;
+    else atomicAdd(&d.sc->prune_overflow, 1u);
+}
 
 }  // namespace abnn

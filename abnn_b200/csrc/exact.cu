@@ -51,11 +51,13 @@ __global__ void __launch_bounds__(256) k_exact_phase1(const __grid_constant__ KP
         u32 dst = 0;
         if (i < kp.count && sample_edge(kp, event_base, i, &edge)) {
             const uint4 s = __ldcs(reinterpret_cast<const uint4*>(d.syn + edge));
-            const u64 now = kp.clock_mode == ABNN_CLOCK_PER_PASS ? clock : clock + i * kp.world + kp.rank;
-            if (kp.track_visits) atomicMax(d.visited + s.y, now);
-            const u64 lp = __ldcg(d.view + s.x);
-            cand = now - lp <= kp.window_pre;
-            dst = s.y;
+            if (s.x != DEAD_SRC) {                                   // a dead record waits for the next rebuild: no event
+                const u64 now = kp.clock_mode == ABNN_CLOCK_PER_PASS ? clock : clock + i * kp.world + kp.rank;
+                if (kp.track_visits) atomicMax(d.visited + s.y, now);
+                const u64 lp = __ldcg(d.view + s.x);
+                cand = now - lp <= kp.window_pre;
+                dst = s.y;
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, cand);
         if (!m) continue;
@@ -109,7 +111,9 @@ __global__ void __launch_bounds__(256) k_exact_phase3(const __grid_constant__ KP
             const float isi = (float)(now - ld);                           // brain.metal:116
             const float est = isi > 0.f ? kp.home_tick_hz / isi : 0.f;     // brain.metal:117
             dW += kp.eta_home * (kp.target_rate_hz - est) * w;             // brain.metal:118
-            d.syn[edge].w = clampf(w + dW, kp.w_min, kp.w_max);            // brain.metal:121-122
+            const float w_new = clampf(w + dW, kp.w_min, kp.w_max);        // brain.metal:121
+            d.syn[edge].w = w_new;                                         // brain.metal:122
+            stage_prune(kp, d, edge, w_new);
             ++gated;
             if (fired) {
                 if (ld < now) ld = now;                                    // brain.metal:125-126

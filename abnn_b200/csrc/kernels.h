@@ -88,6 +88,8 @@ cudaError_t launch_compact_two_pass(const CompactArgs& a, void* scratch, u64* d_
 size_t grow_sort_scratch_bytes(u32 n);
 cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 dst_lo, u32 dst_hi, u32* d_owned, void* scratch, cudaStream_t st);
 cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st);
+// compact_every > 1: staged prune candidates list[0..n) that are still below w_prune become dead in place; *n_marked = how many
+cudaError_t launch_mark_dead(const u64* list, u32 n, abnn_synapse* syn, float w_prune, u64* n_marked, cudaStream_t st);
 
 // Stable sort of n records by dst (ABNN_TABLE_DST_SORTED). alt/keys/keys_alt: n-element scratch buffers.
 // The sorted table ends up in `alt` when *result_in_alt (the caller copies it back), else in `syn`.

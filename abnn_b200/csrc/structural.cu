@@ -490,6 +490,23 @@ cudaError_t launch_grow_sort_count(GrowCand* c, u32 n, u32 dst_lo, u32 dst_hi, u
         e = cudaMemcpyAsync(c, v.Current(), (size_t)n * sizeof(uint4), cudaMemcpyDeviceToDevice, st);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
+// compact_every > 1: the staged prune candidates (records written below w_prune since the last structural step) that are
+// still below it become dead in place; *n_marked counts them (a record staged twice is marked once).
+__global__ void k_mark_dead(const u64* __restrict__ list, u32 n, abnn_synapse* syn, float w_prune, u64* n_marked)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    abnn_synapse* r = syn + list[i];
+    if (r->w < w_prune && atomicExch(&r->src, DEAD_SRC) != DEAD_SRC) atomicAdd(n_marked, 1ull);
+}
+cudaError_t launch_mark_dead(const u64* list, u32 n, abnn_synapse* syn, float w_prune, u64* n_marked, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(n_marked, 0, sizeof(u64), st);
+    if (e != cudaSuccess || !n) return e;
+    k_mark_dead<<<(n + 255) / 256, 256, 0, st>>>(list, n, syn, w_prune, n_marked);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st)
 {
     if (!m) return cudaSuccess;

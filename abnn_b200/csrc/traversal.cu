@@ -104,6 +104,7 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
         }
         const u64 now = event_now(kp, clock, i);
         const abnn_synapse s = d.syn[edge];
+        if (s.src == DEAD_SRC) continue;                                      // pruned, waiting for the next rebuild
         if (kp.track_visits && d.visited[s.dst] < now) d.visited[s.dst] = now;
         const u64 lp = d.view[s.src];
         if (now - lp > kp.window_pre) continue;
@@ -118,6 +119,7 @@ __global__ void k_traverse_serial(const __grid_constant__ KParams kp, const DevP
         if (kp.rbar_mode == ABNN_RBAR_METAL_TID0 && i == 0 && kp.rank == 0)
             rbar = rbar + kp.alpha_rbar * (R - rbar);                         // brain.metal:110-113
         d.syn[edge].w = w;                                                    // brain.metal:122
+        stage_prune(kp, d, edge, w);
         ++gated;
         if (fired) {
             if (d.live[s.dst] < now) d.live[s.dst] = now;                     // brain.metal:125-126
@@ -164,7 +166,9 @@ __device__ __forceinline__ u32 candidate_turn(const KParams& kp, const DevPtrs& 
         const u32 old = atomicAdd(&d.sc->fires_claimed, 1u);
         if (old >= kp.budget_share) { fired = false; atomicSub(&d.sc->fires_claimed, 1u); }
     }
-    __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, gap));                   // brain.metal:122
+    const float w_new = plasticity(kp, w, fired, pc.R, pc.rbar, gap);
+    __stcg(&d.syn[edge].w, w_new);                                                          // brain.metal:122
+    stage_prune(kp, d, edge, w_new);
     if (!fired) return 1;
     atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
     stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.trial);
@@ -228,7 +232,9 @@ __device__ __forceinline__ u32 chain_resolve(const KParams& kp, const DevPtrs& d
         }
     } while (__any_sync(cmask, !settled));
     if (skip) return 0;
-    __stcg(&d.syn[edge].w, plasticity(kp, w, fired, pc.R, pc.rbar, gap));                   // brain.metal:122
+    const float w_new = plasticity(kp, w, fired, pc.R, pc.rbar, gap);
+    __stcg(&d.syn[edge].w, w_new);                                                          // brain.metal:122
+    stage_prune(kp, d, edge, w_new);
     if (!fired) return 1;
     atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
     stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.trial);
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
         }
 #pragma unroll
         for (int j = 0; j < U; ++j)
-            if (ok[j]) s[j] = load_synapse(d.syn + edge[j]);                     // brain.metal:70
+            if (ok[j]) { s[j] = load_synapse(d.syn + edge[j]); ok[j] = s[j].x != DEAD_SRC; }   // brain.metal:70
 #pragma unroll
         for (int j = 0; j < U; ++j)
             if (ok[j]) lp[j] = window_word(kp, d, s[j].x);                       // brain.metal:73
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
                 ev[kk] = ((c * 32 + src_lane) << LOGB) + rec;
                 ed[kk] = b + rec;
                 ok[kk] = b != ~0ull && ev[kk] < kp.count && ed[kk] < kp.n_local;
-                if (ok[kk]) s[kk] = load_synapse(d.syn + ed[kk]);
+                if (ok[kk]) { s[kk] = load_synapse(d.syn + ed[kk]); ok[kk] = s[kk].x != DEAD_SRC; }
             }
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk)
@@ -583,7 +589,8 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 ts[j] = 0; gate[j] = 0;
                 if ((okm >> k) & 1u) {
                     const uint2 sd = *reinterpret_cast<const uint2*>(mine + k * 512);
-                    if (SLACK) {
+                    if (sd.x == DEAD_SRC) okm &= ~(1u << k);                                // pruned, waiting for the next rebuild
+                    else if (SLACK) {
                         gate[j] = __ldcg(d.slack + sd.x);                                   // brain.metal:73 (32-bit form)
                         ts[j] = __ldcg(d.live + sd.y);                                      // brain.metal:79
                     } else {
@@ -836,8 +843,11 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 gate[j] = 0; fire[j] = 0;
                 if ((okm >> k) & 1u) {
                     const uint2 sd = *reinterpret_cast<const uint2*>(mine + k * 512);
-                    gate[j] = __ldcg(d.slack + sd.x);                                       // brain.metal:73 (32-bit form)
-                    fire[j] = __ldcg(d.fire32 + sd.y);                                      // brain.metal:79 (32-bit form)
+                    if (sd.x == DEAD_SRC) okm &= ~(1u << k);                                // pruned, waiting for the next rebuild
+                    else {
+                        gate[j] = __ldcg(d.slack + sd.x);                                   // brain.metal:73 (32-bit form)
+                        fire[j] = __ldcg(d.fire32 + sd.y);                                  // brain.metal:79 (32-bit form)
+                    }
                 }
             }
 #pragma unroll
@@ -957,7 +967,9 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                     const u64 ld = __ldcg(d.live + sy.y), now = clock + t;
                     isi = (float)(ld <= now ? now - ld : ld - now);
                 }
-                __stcg(&d.syn[edge].w, plasticity_f(kp, w, fired, R, rbar, isi));           // brain.metal:101-122
+                const float w_new = plasticity_f(kp, w, fired, R, rbar, isi);               // brain.metal:101-121
+                __stcg(&d.syn[edge].w, w_new);                                              // brain.metal:122
+                stage_prune(kp, d, edge, w_new);
             }
             if (fired) {
                 atomicMax(d.fire32 + sy.y, (int)t);                                         // brain.metal:125-126

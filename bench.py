@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--no-visits", action="store_true")
     ap.add_argument("--no-l2-persist", action="store_true")
     ap.add_argument("--structural", action="store_true", help="BASELINE configs[4]: prune + grow after every pass")
+    ap.add_argument("--compact-every", type=int, default=16,
+                    help="--structural: abnn_params.compact_every (1 = rebuild the table at every structural step; K > 1 = mark dead in "
+                         "place + append behind the table, rebuild every K-th step: README.md:122-124 'compact periodically')")
     ap.add_argument("--cpu-syn", type=int, default=0, help="table of the CPU arm (default: the GPU arm's when the host has the memory, else 1e8)")
     ap.add_argument("--cpu-events", type=int, default=0, help="events per CPU step (default: sized for about 20-90 s in total)")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -250,7 +253,7 @@ def workload_params(args, p, rank, world, events, **over):
                 exchange=capi.EXCHANGE_PEER if args.exchange == "peer" else capi.EXCHANGE_NCCL)
     if args.structural:                              # configs[4]: Beta(2,8) weights, ~7 % below 0.05 at the start
         share = args.syn // world
-        vals.update(w_prune=0.05, p_new=0.25, w_init=0.1, syn_capacity=share + (share >> 5) + (1 << 20))
+        vals.update(w_prune=0.05, p_new=0.25, w_init=0.1, syn_capacity=share + (share >> 5) + (1 << 20), compact_every=args.compact_every)
     vals.update(over)
     for k, v in vals.items():
         setattr(p, k, v)
@@ -603,10 +606,12 @@ def main():
         }
         if args.structural:
             line["structural"] = {"ms_per_structural_step": struct_mean, "fraction_of_step": struct_mean / ms_step if ms_step else None,
+                                  "compact_every": args.compact_every, "ms_per_structural_step_max": float(np.max(struct_ms)) if struct_ms else None,
                                   "n_syn_after": n_after, "pruned_last": int(struct_last.pruned) if struct_last else None,
                                   "appended_last": int(struct_last.appended) if struct_last else None,
                                   # stable compaction + sorted insertion out of place: 16 B read (count) + 16 B read + 16 B written per record
-                                  "sweep_roofline_frac": (48.0 * n_after / world) / (struct_mean * 1e-3) / 1e9 / peak if struct_mean else None,
+                                  "sweep_roofline_frac": ((48.0 * n_after / world) / (struct_mean * 1e-3) / 1e9 / peak
+                                                          if struct_mean and args.compact_every <= 1 else None),
                                   "note": "ms_per_step includes the structural step (the device timer spans the synchronising abnn_prune_and_grow)"}
         if parity is not None:
             line["parity"] = parity

@@ -194,7 +194,18 @@ typedef struct abnn_params {
                                       scatter passes, every tile independent), else in place; 1: always in place (single-
                                       pass chained scan: no second table, about 1.7x slower)                          */
     uint32_t exchange;             /* abnn_exchange: how sharded PARALLEL runs publish their gate words after a pass    */
+    uint32_t compact_every;        /* structural steps between two rebuilds of the table. 0 / 1: every abnn_prune_and_grow is a
+                                      stable prune-compaction + ordered (sorted) insertion. K > 1 — README.md:122-124 "remove,
+                                      compact PERIODICALLY": steps 0, K, 2K, ... (counted since the table was uploaded /
+                                      initialised / loaded) rebuild the table like that; the steps in between touch only what
+                                      changed: a record whose weight fell below w_prune is marked dead IN PLACE (src =
+                                      0xFFFFFFFF; its slot stays, an event that samples it does nothing) and the grown synapses
+                                      are appended behind the table in tick order, to be merged into their destination's run by
+                                      the next rebuild. Needs w_init >= w_prune.                                              */
+    uint32_t reserved_;
 } abnn_params;
+
+#define ABNN_DEAD_SRC 0xFFFFFFFFu   /* abnn_synapse.src of a pruned record that waits for the next rebuild (compact_every > 1) */
 
 #define ABNN_MAX_FIR 64u
 

@@ -86,6 +86,8 @@ struct ob_handle {
     float reward = 0.f, rbar = 0.f;
     std::vector<GrowCand> grow;
     uint64_t grow_dropped = 0;
+    // structural plasticity with periodic rebuilds (abnn_params.compact_every > 1, include/abnn.h)
+    uint64_t struct_steps = 0, n_dead = 0;
     // read-out state (brain-engine.cpp:145-186, rate-filter.h)
     std::vector<float> rate, iir;
     std::vector<std::vector<float>> fir;
@@ -102,6 +104,9 @@ void recount(ob_handle* h)
 {
     if (h->p.world_size == 1) h->n_local_all.assign(1, h->syn.size());
 }
+bool lazy_mode(const ob_handle* h) { return h->p.compact_every > 1; }
+bool rebuild_step(const ob_handle* h) { return !lazy_mode(h) || h->struct_steps % h->p.compact_every == 0; }
+void new_table(ob_handle* h) { h->struct_steps = 0; h->n_dead = 0; }
 
 // ABNN_TABLE_DST_SORTED (include/abnn.h): stable sort of the shard's table by dst (counting sort:
 // records with equal dst keep their relative order). No reference counterpart — a layout rule of
@@ -211,6 +216,7 @@ int ob_upload_synapses(ob_handle* h, const abnn_synapse* s, uint64_t n)
     if (h->syn.size() > h->cap) return ABNN_ERR_CAPACITY;
     sort_table(h);
     recount(h);
+    new_table(h);
     return 0;
 }
 int ob_download_synapses(ob_handle* h, abnn_synapse* out, uint64_t cap, uint64_t* n_out)
@@ -286,6 +292,7 @@ int ob_init_graph(ob_handle* h, uint32_t kind, uint64_t seed)
                                     uint64_t((unsigned __int128)p.n_syn * k / p.world_size);
         sort_table(h);
         recount(h);
+        new_table(h);
         return 0;
     }
     return ABNN_ERR_INVALID;
@@ -381,6 +388,7 @@ int ob_run_pass(ob_handle* h, uint64_t events, abnn_pass_stats* st)
         // K2: clock
         const uint64_t now = p.clock_mode == ABNN_CLOCK_PER_PASS ? h->clock : h->clock + i * G + k;
         abnn_synapse s = h->syn[edge];                           // brain.metal:70
+        if (s.src == ABNN_DEAD_SRC) continue;                    // pruned, waiting for the next rebuild: the event does nothing
         if (p.track_visits && h->lastV[s.dst] < now) h->lastV[s.dst] = now;   // README.md:84
         // K3: gating
         const uint64_t lp = srcv[s.src];
@@ -500,16 +508,28 @@ int ob_get_loss(ob_handle* h, double* l, uint64_t* w) { if (l) *l = h->last_loss
 
 // ---- structural plasticity (README.md:120-127) ------------------------------------------------
 // Prune: remove records with w < w_prune, order preserved. Returns number removed.
+// With compact_every = K > 1 (README.md:122-124 "remove, compact periodically") only the structural steps 0, K, 2K, ...
+// since the table was made remove records; in between a pruned record is marked dead in place (src = ABNN_DEAD_SRC, its
+// slot is still sampled, the event does nothing). Returns the number of records that were alive and are pruned now.
 uint64_t ob_prune(ob_handle* h)
 {
     const float wp = h->p.w_prune;
     if (!(wp > 0.f)) return 0;
     const size_t n0 = h->syn.size();
+    if (!rebuild_step(h)) {
+        uint64_t marked = 0;
+        for (auto& s : h->syn)
+            if (s.src != ABNN_DEAD_SRC && s.w < wp) { s.src = ABNN_DEAD_SRC; ++marked; }
+        h->n_dead += marked;
+        return marked;
+    }
     size_t o = 0;
-    for (size_t i = 0; i < n0; ++i) if (!(h->syn[i].w < wp)) h->syn[o++] = h->syn[i];
+    for (size_t i = 0; i < n0; ++i) if (!(h->syn[i].w < wp)) h->syn[o++] = h->syn[i];   // dead records carry w < w_prune
     h->syn.resize(o);
     if (o != n0 && h->p.table_order == ABNN_TABLE_DST_INTERLEAVED) sort_table(h);   // the interleaved order is re-derived after every change
-    return n0 - o;
+    const uint64_t pruned = (n0 - h->n_dead) - o;
+    h->n_dead = 0;
+    return pruned;
 }
 // Staged growth candidates of this shard: (order, src, dst) triples, 16 bytes each.
 uint64_t ob_grow_count(ob_handle* h) { return h->grow.size(); }
@@ -527,7 +547,10 @@ uint64_t ob_grow_apply(ob_handle* h, const void* cands, uint64_t n, uint64_t* dr
         ++app;
     }
     h->grow.clear();
-    if (app) sort_table(h);
+    // eager mode / rebuild step: the new records go to their place in the table order (stable: behind the existing records of
+    // their destination, tail records of earlier lazy steps first); lazy step: they stay behind the table, in tick order
+    if (rebuild_step(h) ? (app || lazy_mode(h)) : false) sort_table(h);
+    h->struct_steps += 1;
     if (dropped) *dropped = drop;
     return app;
 }

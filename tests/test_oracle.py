@@ -293,3 +293,34 @@ def test_logger_matches_the_reference_logger_byte_for_byte(tmp_path):
     for l in range(10):
         ema = 0.25 / (l + 1) if l == 0 else 0.98 * ema + (1.0 - 0.98) * 0.25 / (l + 1)          # logger.cpp:61-62
     assert abs(float(r.stdout.strip().splitlines()[-1].split()[1]) - ema) < 1e-15
+
+
+def test_oracle_periodic_rebuild_schedule():
+    """compact_every = 3 in the oracle: structural steps 0, 3, 6 rebuild (no dead record, table in dst order), the steps in
+    between keep every slot (dead records stay, grown synapses sit behind the table) and only the rebuild shrinks it."""
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(3)
+    N, n = 2000, 40_000
+    syn = np.zeros(n, O.SYN_DTYPE)
+    syn["src"] = rng.integers(0, N, n); syn["dst"] = rng.integers(16, N, n); syn["w"] = rng.uniform(0.15, 1.0, n).astype(np.float32)
+    p = O.default_params(capi.PROFILE_NORTH_STAR, n_input=8, n_output=8, n_hidden=N - 16, n_syn=n, exec_mode=capi.EXEC_SERIAL, sample_block=8,
+                         table_order=capi.TABLE_DST_SORTED, window_pre=400_000, refractory=5_000, p_new=0.3, w_prune=0.16, w_init=0.17,
+                         syn_capacity=n + 20_000, compact_every=3)
+    o = O.OracleB(p)
+    o.upload_synapses(syn); o.upload_timestamps(rng.integers(1, 20_000, N).astype(np.uint64), None); o.clock = 20_000; o.set_reward(0.1)
+    dead_total = 0
+    for step in range(7):
+        o.run_pass(30_000)
+        before = o.download_synapses()
+        st = o.prune_and_grow()
+        t = o.download_synapses()
+        dead = int((t["src"] == 0xFFFFFFFF).sum())
+        if step % 3 == 0:
+            assert dead == 0 and np.all(np.diff(t["dst"].astype(np.int64)) >= 0)
+            assert st.n_after == len(t) <= st.n_before + st.appended
+        else:
+            assert st.n_after == st.n_before + st.appended == len(t)
+            assert t[:len(before)]["dst"].tobytes() == before["dst"].tobytes()       # nothing moved
+            assert np.all(t[len(before):]["w"] == np.float32(0.17))                  # the tail holds the grown synapses
+            dead_total += dead
+    assert dead_total > 0
