@@ -114,6 +114,7 @@ struct abnn_handle {
     cudaGraphExec_t step_exec = nullptr;
     u64 step_events = 0; std::vector<u64> step_counts; bool step_pre[3]{}, step_post[3]{};
     u64 step_calls = 0, step_replays = 0;
+    u64 last_events = 0; std::vector<u64> last_counts; bool last_pre[3]{};   // key of the previous abnn_engine_step call
     bool slack_ready = false;             // d.slack already holds the next pass's gate words (all but the in/out head)
     bool fire_ready = false;              // d.fire32 / d.vis32 of the owned neurons are prepared for the next pass (all but the head)
     bool view_stale = false;              // remote slices of d.view were not refreshed by the last exchange
@@ -1377,12 +1378,19 @@ int abnn_engine_step(abnn_handle* h, const float* in, const float* expected, flo
     const bool capturable = ((h->p.exec_mode == ABNN_EXEC_PARALLEL && (h->p.world_size == 1 || sharded_ok)) || exact_ok) && !no_graph;
     const bool match = h->step_exec && h->step_events == events && h->step_counts == h->n_local_all &&
                        h->step_pre[0] == pre[0] && h->step_pre[1] == pre[1] && h->step_pre[2] == pre[2];
+    // record a graph only for a state that has just repeated (same events / table sizes / word state as the previous call):
+    // a run whose table changes every step (structural plasticity after every pass) enqueues eagerly instead of
+    // re-capturing every time
+    const bool repeated = h->step_calls > 0 && h->last_events == events && h->last_counts == h->n_local_all &&
+                          h->last_pre[0] == pre[0] && h->last_pre[1] == pre[1] && h->last_pre[2] == pre[2];
+    h->last_events = events; h->last_counts = h->n_local_all;
+    h->last_pre[0] = pre[0]; h->last_pre[1] = pre[1]; h->last_pre[2] = pre[2];
     ++h->step_calls;
     if (capturable && match) {
         CU(cudaGraphLaunch(h->step_exec, h->st));
         h->slack_ready = h->step_post[0]; h->view_stale = h->step_post[1]; h->fire_ready = h->step_post[2];
         ++h->step_replays;
-    } else if (capturable && h->step_calls > 1) {
+    } else if (capturable && repeated) {
         // second call onwards (the first one warms up lazily configured kernels): record this state's
         // sequence once, then replay it for as long as events / table size / exchange state repeat
         if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }
@@ -1493,10 +1501,11 @@ int abnn_get_loss(abnn_handle* h, double* last_loss, uint64_t* windows_done)
 namespace {
 // Growth candidates staged since the last structural step, from every rank, sorted by the tick ordinal of the firing
 // event; *owned = how many of them target this rank's neurons (they sort first). Collective when world_size > 1.
-int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out, bool other_overflow = false)
+int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out, bool other_overflow = false, const DevScalars* have = nullptr)
 {
     *list_out = h->d.grow; *owned_out = 0;
-    DevScalars sc; RET(read_scalars(h, &sc));
+    DevScalars sc;
+    if (have) sc = *have; else RET(read_scalars(h, &sc));
     bool overflow = sc.grow_overflow != 0 || other_overflow;      // (the prune staging buffer of compact_every > 1 shares the agreement)
     u32 n = std::min(sc.grow_count, h->grow_cap);
     GrowCand* list = h->d.grow;
@@ -1673,7 +1682,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
     // growth candidates first (they do not depend on the table): their number decides how the table is rewritten
     GrowCand* list = nullptr;
     u32 owned = 0;
-    if (grow) RET(gather_growth(h, &list, &owned, lazy && sc.prune_overflow != 0));
+    if (grow) RET(gather_growth(h, &list, &owned, lazy && sc.prune_overflow != 0, lazy ? &sc : nullptr));
     else if (lazy && sc.prune_overflow) {
         k_set_struct<<<1, 1, 0, h->st>>>(h->d.sc, h->struct_steps, h->n_sorted, h->n_dead);
         return fail(ABNN_ERR_CAPACITY, "prune staging buffer overflowed; call abnn_prune_and_grow more often");

@@ -9,7 +9,8 @@ traversal events -> (N>1) exchange of the fired-neuron timestamps -> FIR read-ou
 BASELINE.json configs[2] (the shape the metric is quoted on): 5,000,000 hidden + 256 in + 256 out neurons, 1,000,000,000
 synapses (16 GB SynapsePacked), 150,000,000 events per pass; for N>1 the same table is dst-sharded over the ranks
 (configs[3], strong scaling). --structural runs BASELINE configs[4] instead: pruning + synaptogenesis after EVERY pass,
-4,000,000,000 synapses at N=8 (500M per GPU; at smaller N the same 500M per GPU), weak scaling.
+4,000,000,000 synapses, 5M hidden neurons and 150M-event passes at N=8; at smaller N the same per-GPU load (500M synapses,
+625k hidden neurons and 18.75M events per pass and GPU), weak scaling.
 
   value    : whole-job events/s, device-timed (CUDA events on the handle's stream), state resident in HBM.
   e2e      : the same through the reference-facing per-pass API with HOST buffers: stimulus vectors are copied
@@ -53,9 +54,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--hidden", type=int, default=5_000_000)
+    ap.add_argument("--hidden", type=int, default=0, help="hidden neurons (default: 5M; --structural: 5M * gpus / 8, the per-GPU load of configs[4])")
     ap.add_argument("--syn", type=int, default=0, help="global synapse count (default: 1e9; --structural: 5e8 per GPU)")
-    ap.add_argument("--events", type=int, default=150_000_000)
+    ap.add_argument("--events", type=int, default=0, help="events per pass (default: 150M; --structural: 150M * gpus / 8, the per-GPU load of configs[4])")
     ap.add_argument("--sampler", default="philox", choices=["philox", "sweep"])
     ap.add_argument("--block", type=int, default=16, help="PHILOX sampler granularity in records (16 = 256 bytes = two 128-byte HBM lines per draw; 1 = iid)")
     ap.add_argument("--table-order", default="interleaved", choices=list(TABLE_ORDERS),
@@ -78,6 +79,10 @@ def parse():
     a = ap.parse_args()
     if not a.syn:
         a.syn = 500_000_000 * max(1, a.gpus) if a.structural else 1_000_000_000
+    if not a.events:
+        a.events = 150_000_000 * max(1, a.gpus) // 8 if a.structural else 150_000_000
+    if not a.hidden:
+        a.hidden = 5_000_000 * max(1, a.gpus) // 8 if a.structural else 5_000_000
     return a
 
 

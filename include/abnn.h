@@ -299,8 +299,9 @@ int abnn_sync(abnn_handle* h);                                           /* wait
 /* One whole engine pass without a host round trip — BrainEngine::run_one_pass (brain-engine.cpp:108-190):
  * stage the stimulus frame, inject_inputs(in, hz), teacher forcing (expected, teacher_rate), `events`
  * traversal events, timestamp exchange, read-out step with loss/reward. Equivalent to abnn_inject_inputs +
- * abnn_teacher_force + abnn_run_pass(NULL) + abnn_readout_step; the device work is recorded into a CUDA graph on
- * the second call and replayed while events / table size stay the same: PARALLEL and EXACT execution on single-GPU
+ * abnn_teacher_force + abnn_run_pass(NULL) + abnn_readout_step; the device work is recorded into a CUDA graph once a
+ * call repeats the state of the one before it (same events, table sizes and word state: the third call of a steady
+ * run) and replayed while that stays the same: PARALLEL and EXACT execution on single-GPU
  * handles, PARALLEL on sharded handles with exchange = ABNN_EXCHANGE_PEER (with the NCCL exchange sharded handles
  * enqueue the same sequence eagerly).
  * Asynchronous when rates == NULL; otherwise writes the n_output filtered rates and synchronises. */

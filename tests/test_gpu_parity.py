@@ -337,7 +337,7 @@ def test_parallel_conflict_free_is_bit_exact():
 
 def test_engine_step_graph_replay_is_bit_exact():
     """abnn_engine_step (stage frame + inject + teacher forcing + pass + read-out as one call, recorded into a CUDA
-    graph on the second call and replayed afterwards) on a conflict-free PARALLEL workload: every pass equals
+    graph once the state repeats — the third call — and replayed afterwards) on a conflict-free PARALLEL workload: every pass equals
     the oracle driven by the separate calls, bit for bit, and the replay really happened."""
     rng = np.random.default_rng(12)
     N = 1 << 15
