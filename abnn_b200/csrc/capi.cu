@@ -229,7 +229,8 @@ bool slack_mode(const abnn_handle* h, const KParams& kp)
     const bool kernel_reads_slack = kp.sampler == ABNN_SAMPLER_PHILOX && kp.snapshot;
     return h->p.exec_mode == ABNN_EXEC_PARALLEL && h->d.slack && kernel_reads_slack && kp.ticks < 0xFFFFFFF0ull && !off;
 }
-// k_traverse_line32 runs this pass: gate words in use and the kernel's own preconditions (traversal.cu:line32_selected)
+// This pass runs on the 32-bit pass-relative words (k_traverse_line32, or the iid / block kernel in their 32-bit form): gate
+// words in use and the words' own preconditions (traversal.cu:line32_selected)
 bool line32_mode(const abnn_handle* h, const KParams& kp)
 {
     static const bool off = tune_env("ABNN_NO_LINE32") != nullptr;

@@ -161,7 +161,7 @@ struct KParams {
     float base_scale, a_ltp, a_ltd, w_min, w_max, eta_home, target_rate_hz, home_tick_hz, eta_reward, alpha_rbar;
     float p_new;
     u32 use_slack;       // the line kernel reads DevPtrs::slack instead of the 64-bit snapshot
-    u32 use_line32;      // k_traverse_line32 runs this pass (32-bit pass-relative timestamps)
+    u32 use_line32;      // the pass runs on the 32-bit pass-relative words fire32 / vis32 (k_traverse_line32, iid and block kernels)
     u32 lazy_prune;      // compact_every > 1: a weight written below w_prune stages its record for the next structural step
     u32 prune_cap;
     float w_prune;

@@ -236,7 +236,8 @@ __device__ __forceinline__ u32 chain_resolve(const KParams& kp, const DevPtrs& d
     __stcg(&d.syn[edge].w, w_new);                                                          // brain.metal:122
     stage_prune(kp, d, edge, w_new);
     if (!fired) return 1;
-    atomicMax(d.live + dst, now);                                                           // brain.metal:125-126
+    if (kp.use_line32) atomicMax(d.fire32 + dst, (int)(now - pc.clock));                    // brain.metal:125-126 (32-bit form)
+    else atomicMax(d.live + dst, now);                                                      // brain.metal:125-126
     stage_growth(kp, d, eid, pc.tick_base + i * kp.world + kp.rank, src, r.trial);
     return 3;
 }
@@ -244,7 +245,12 @@ __device__ __forceinline__ u32 chain_path(const KParams& kp, const DevPtrs& d, c
                                           u64 edge, u32 src, u32 dst, float w, u64 now)
 {
     u64 ld = 0;
-    if (cand) ld = __ldcg(d.live + dst);                                                    // brain.metal:79
+    if (cand) {
+        if (kp.use_line32) {                             // 32-bit pass-relative fire word; beyond 2^30 ticks the 64-bit array is the truth
+            const int fv = __ldcg(d.fire32 + dst);
+            ld = (fv == FIRE32_ANCIENT || fv == FIRE32_FUTURE) ? __ldcg(d.live + dst) : pc.clock + (u64)(long long)fv;
+        } else ld = __ldcg(d.live + dst);                                                   // brain.metal:79
+    }
     return chain_resolve(kp, d, pc, cand, i, edge, src, dst, w, now, ld);
 }
 
@@ -266,6 +272,14 @@ __device__ __forceinline__ void visit(const DevPtrs& d, bool ok, u32 dst, u64 no
     const u32 key = ok ? dst : 0xFFFFFFFFu;
     const u32 next = __shfl_down_sync(0xffffffffu, key, 1);
     if (ok && ((threadIdx.x & 31) == 31 || next != key)) atomicMax(d.visited + dst, now);   // RED.MAX.64 at L2
+}
+
+// the same on the 32-bit visit words of a pass (1 + latest tick offset; folded into lastVisited by k_fold_prepare32)
+__device__ __forceinline__ void visit32(const DevPtrs& d, bool ok, u32 dst, u32 t)
+{
+    const u32 key = ok ? dst : 0xFFFFFFFFu;
+    const u32 next = __shfl_down_sync(0xffffffffu, key, 1);
+    if (ok && ((threadIdx.x & 31) == 31 || next != key)) atomicMax(d.vis32 + dst, t + 1u);
 }
 
 __device__ __forceinline__ void flush_counters(const DevPtrs& d, u32 n_cand, u32 n_gated, u32 n_fired, u32* s_cnt)
@@ -354,7 +368,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_parallel(c
         for (int j = 0; j < U; ++j) {
             const u64 i = base + (u64)j * 256 + threadIdx.x;
             const u64 now = event_now(kp, pc.clock, i);
-            if (VISITS) visit(d, ok[j], s[j].y, now);                            // README.md:84
+            if (VISITS) { if (kp.use_line32) visit32(d, ok[j], s[j].y, (u32)(now - pc.clock)); else visit(d, ok[j], s[j].y, now); }   // README.md:84
             const bool cand = window_test(kp, d, ok[j], s[j].x, lp[j], now, pc.clock);           // brain.metal:74
             const u32 r = resolve_candidates(kp, d, pc, cand, i, edge[j], s[j].x, s[j].y, __uint_as_float(s[j].z), now);
             n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(256, ABNN_TRAV_MIN_CTAS) k_traverse_block(cons
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk) {
                 const u64 now = event_now(kp, pc.clock, ev[kk]);
-                if (VISITS) visit(d, ok[kk], s[kk].y, now);
+                if (VISITS) { if (kp.use_line32) visit32(d, ok[kk], s[kk].y, (u32)(now - pc.clock)); else visit(d, ok[kk], s[kk].y, now); }
                 const bool cand = window_test(kp, d, ok[kk], s[kk].x, lp[kk], now, pc.clock);
                 const u32 r = resolve_candidates(kp, d, pc, cand, ev[kk], ed[kk], s[kk].x, s[kk].y, __uint_as_float(s[kk].z), now);
                 n_cand += cand; n_gated += r & 1u; n_fired += r >> 1;
@@ -1205,17 +1219,26 @@ bool line_kernel_selected(const KParams& kp)
     static const bool legacy_block = tune_env("ABNN_TRAV_LEGACY_BLOCK") != nullptr;      // A/B measurements only
     return kp.sampler == ABNN_SAMPLER_PHILOX && kp.sample_block == 8 && !legacy_block;
 }
-// k_traverse_line32's preconditions (see its header); the caller additionally needs the gate words (slack_mode)
+// Can this pass run on the 32-bit pass-relative words (slack32 / fire32 / vis32)? Preconditions of the words themselves
+// (per-event clock, snapshot src view, no spike budget, ticks and refractory below 2^30; the caller additionally needs the
+// gate words: slack_mode) and a kernel that works on them: k_traverse_line32 (sample_block 8 / 16, refractory >= one
+// chunk), the iid kernel (sample_block 1) or the block kernel (everything else except sample_block 8, which the 64-bit
+// line kernel serves when the refractory period is shorter than a chunk).
+static bool line32_kernel(const KParams& kp)
+{
+    return (kp.sample_block == 8 || kp.sample_block == 16) && kp.refractory >= (u64)LINE32_EPC * kp.world;
+}
 bool line32_selected(const KParams& kp)
 {
     const u64 lim = 1ull << 30;
-    return kp.sampler == ABNN_SAMPLER_PHILOX && (kp.sample_block == 8 || kp.sample_block == 16) && kp.clock_mode == ABNN_CLOCK_PER_EVENT && !kp.budget_on && kp.snapshot &&
-           kp.ticks < lim - 1 && kp.refractory < lim && kp.refractory >= 256ull * kp.world;
+    if (!(kp.sampler == ABNN_SAMPLER_PHILOX && kp.clock_mode == ABNN_CLOCK_PER_EVENT && !kp.budget_on && kp.snapshot &&
+          kp.ticks < lim - 1 && kp.refractory < lim)) return false;
+    return line32_kernel(kp) || kp.sample_block != 8;
 }
 cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm_count, cudaStream_t st)
 {
     const bool ph = kp.sampler == ABNN_SAMPLER_PHILOX, vis = kp.track_visits != 0;
-    if (kp.use_line32) {
+    if (kp.use_line32 && line32_kernel(kp)) {
         const bool grow = kp.p_new > 0.f;
         if (kp.sample_block == 16) {
             if (vis) return grow ? launch_line32<1, 1, 16>(kp, d, sm_count, st) : launch_line32<1, 0, 16>(kp, d, sm_count, st);
