@@ -485,7 +485,9 @@ cudaError_t launch_build_slack(const KParams& kp, const DevPtrs& d, const u64* s
 //      instead of with the ~quarter of lanes that are open in a raw step; lastFired[dst] of step j+1 is
 //      fetched before step j is resolved. Same-destination events are ordered inside a step by
 //      chain_resolve and across the steps of a chunk by a small shared-memory list of the chunk's
-//      fires, so a warp's 256 events resolve exactly as in the serial order.
+//      fires, so a warp's 256 events resolve exactly as in the serial order — with one exception in THIS kernel: two
+//      groups of a chunk that drew the same line and whose events land in the same dense step both use the weight read
+//      before either wrote (tables of a few hundred lines only; k_traverse_line32 cuts the step instead).
 //
 // Shared memory is kept to 4.5 KB per warp on purpose. Measured on B200 (profiles/r1_notes.md): the
 // gathers of this kernel are limited by the L1's capacity to track outstanding misses, i.e. by what the
