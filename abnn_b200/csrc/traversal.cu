@@ -733,6 +733,12 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
 // (common.cuh:release_word).
 // SB = sample_block: 8 (one 128-byte line per draw) or 16 (two consecutive lines = 256 bytes per draw, the size at which
 // random HBM3e reads reach the copy bandwidth: 6.7 TB/s against 4.7 TB/s for single lines, profiles/r2_notes.md).
+// SB = 1 (iid sampler, README.md:77): the same kernel with one draw per EVENT. A lane makes the 8 Philox calls of its 8
+// events of the chunk and requests their 16-byte records with cp.async — 256 random gathers in flight per warp, 8,192 per
+// SM, none of them holding a register (the register-staged iid kernel k_traverse_parallel keeps 3,072 in flight and runs
+// at 64 % of the bare-gather rate, profiles/r2_notes.md §7). Phases A / B / C are unchanged; a dense step repeats the
+// Philox call of its event for the record index and the release / growth words (28 % of the events get that far). On
+// tables below 2^24 records every dense step checks for records drawn twice in the chunk, as above for lines.
 // Shared memory of a warp: the 4 KB stage, then the records of the chunk's OPEN events compacted in event order (16 B
 // each: src, dst, w, fire word). With the open events copied out, the stage is free as soon as phase B is over, and the
 // NEXT chunk's lines are requested before the dense steps run: the HBM latency of chunk c+1 hides under phase C of chunk
@@ -760,8 +766,9 @@ template <int VISITS, int GROW, int SB>
 __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_traverse_line32(const __grid_constant__ KParams kp, const DevPtrs d)
 {
     constexpr int LOGB = 3, B = 8, PART = ABNN_LINE_PART;     // a LINE is 8 records; a sample group is LPG lines
-    constexpr int LPG = SB / 8, LOGSB = SB == 8 ? 3 : 4;
-    static_assert(SB == 8 || SB == 16, "line kernel: sample_block 8 or 16");
+    constexpr int LPG = SB == 16 ? 2 : 1, LOGSB = SB == 8 ? 3 : 4;
+    constexpr bool IID = SB == 1;                             // one draw per EVENT: see "iid" in the header
+    static_assert(SB == 1 || SB == 8 || SB == 16, "line kernel: sample_block 1, 8 or 16");
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -788,6 +795,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     // lanes of a group evaluate the group's draw (same warp instructions, no shuffle).
     u64 zw = 0, zw_next = 0;
     auto draw = [&](u32 c, u64& zw_out) -> u64 {
+        if (IID) return 0ull;                                // nothing is kept per line: stage_issue / the dense step draw per event
         const u32 i0 = (c * (LINE32_LPC / LPG) + (lane / LPG)) << LOGSB;    // first event of the line's group
         if (c >= n_chunks || lane >= LINE32_LPC || i0 >= count) return ~0ull;
         const Philox4 r = event_philox(kp, event_base + i0);
@@ -811,8 +819,22 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     };
     // request the lines of a chunk (8 LDGSTS.128 per lane, each warp instruction moves 4 whole lines); bit k of the result:
     // this lane's record of step k exists
-    auto stage_issue = [&](u64 mm) -> u32 {
+    auto stage_issue = [&](u64 mm, u32 cc) -> u32 {
         u32 ok = 0;
+        if (IID) {                                           // 8 independent Philox calls and 16-byte copies per lane
+            if (cc >= n_chunks) return 0u;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const u32 i = cc * LINE32_EPC + k * 32 + lane;
+                if (i < count) {
+                    const Philox4 r = event_philox(kp, event_base + i);
+                    ok |= 1u << k;
+                    cp_async16(mine_addr + k * 512, d.syn + mulhi64(((u64)r.x << 32) | r.y, kp.n_local));
+                }
+            }
+            cp_async_commit();
+            return ok;
+        }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const u64 mk = __shfl_sync(0xffffffffu, mm, k * 4 + sub);
@@ -831,12 +853,13 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     const bool check_dups = kp.n_blocks < (1ull << 24);
     auto dup_mask = [&](u64 mm) -> unsigned {
         if (!check_dups) return 0u;
+        if (IID) return 0xFFFFFFFFu;                         // small table: every dense step looks for repeated records
         const unsigned same = __match_any_sync(0xffffffffu, mm);
         return __ballot_sync(0xffffffffu, mm != ~0ull && (same & lt) != 0);
     };
     u32 c = take();
     u64 m = draw(c, zw);
-    u32 okm = stage_issue(m);
+    u32 okm = stage_issue(m, c);
     unsigned dupm = dup_mask(m);
     while (c < n_chunks) {
         const u32 c_next = take();
@@ -917,7 +940,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         const bool in_cq = LINE32_CQ > 0 && nC <= LINE32_CQ;     // the dense steps read the compacted copy
         const bool early = LINE32_EARLY && in_cq;
         u32 okm_next = 0; unsigned dupm_next = 0;
-        if (early) { okm_next = stage_issue(m_next); dupm_next = dup_mask(m_next); }
+        if (early) { okm_next = stage_issue(m_next, c_next); dupm_next = dup_mask(m_next); }
 
         // ---- C: dense steps over the queue ----------------------------------------------------------------
         u32 nf = 0;                                          // destinations that fired in this chunk so far (warp-uniform)
@@ -937,9 +960,17 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 le_n = queue[j + 32 + lane];
                 sy_n = in_cq ? cq[j + 32 + lane] : *reinterpret_cast<const uint4*>(stage + le_n * 16);
             }
-            const u32 g = le >> LOGB, r8 = le & 7u;
-            const u64 edge = (__shfl_sync(0xffffffffu, m, g) & ~7ull) + r8;
-            const u64 zwg = __shfl_sync(0xffffffffu, zw, g);
+            u32 g = le >> LOGB, r8 = le & 7u;
+            u64 edge, zwg;
+            if (IID) {                                       // the event's own draw again (its record came in by cp.async)
+                const Philox4 q = event_philox(kp, event_base + ev0 + le);
+                edge = mulhi64(((u64)q.x << 32) | q.y, kp.n_local);
+                zwg = (u64)q.z | ((u64)q.w << 32);
+                g = le; r8 = 0;
+            } else {
+                edge = (__shfl_sync(0xffffffffu, m, g) & ~7ull) + r8;
+                zwg = __shfl_sync(0xffffffffu, zw, g);
+            }
             const u32 t = t0 + le * world;
             u32 adv = 32;
             if (dupm) {
@@ -948,7 +979,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
                 // in front of the first lane whose line already appears in it under another group; the rest is redone.
                 const unsigned cm0 = __ballot_sync(0xffffffffu, cand);
                 unsigned pe = 1u << lane;
-                if (cand) pe = __match_any_sync(cm0, (u32)(edge >> LOGB));
+                if (cand) pe = __match_any_sync(cm0, IID ? (u32)edge : (u32)(edge >> LOGB));
                 const u32 g_first = __shfl_sync(0xffffffffu, g, __ffs(pe) - 1);
                 const unsigned cut = __ballot_sync(0xffffffffu, cand && g != g_first);
                 if (cut) { adv = __ffs(cut) - 1; cand = cand && lane < adv; }
@@ -957,7 +988,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             bool skip = true, want = false;
             int gap = 0, fv = (int)sy.w;
             if (cand) {
-                if ((dupm >> g) & 1u) w = __ldcg(&d.syn[edge].w);
+                if (IID ? dupm != 0u : ((dupm >> g) & 1u) != 0u) w = __ldcg(&d.syn[edge].w);
                 if (spilled) fv = __ldcg(d.fire32 + sy.y);                                  // brain.metal:79
                 gap = (int)t - fv;
                 skip = (u32)(gap < 0 ? -gap : gap) <= refr;                                 // brain.metal:79-83
@@ -1012,7 +1043,7 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             }
         }
         __syncwarp();                                        // every lane is done with the stage and the queues
-        if (!early) { okm_next = stage_issue(m_next); dupm_next = dup_mask(m_next); }
+        if (!early) { okm_next = stage_issue(m_next, c_next); dupm_next = dup_mask(m_next); }
         c = c_next; m = m_next; zw = zw_next; okm = okm_next; dupm = dupm_next;
     }
     flush_counters(d, n_cand, n_gated, n_fired, s_cnt);
@@ -1223,12 +1254,14 @@ bool line_kernel_selected(const KParams& kp)
 }
 // Can this pass run on the 32-bit pass-relative words (slack32 / fire32 / vis32)? Preconditions of the words themselves
 // (per-event clock, snapshot src view, no spike budget, ticks and refractory below 2^30; the caller additionally needs the
-// gate words: slack_mode) and a kernel that works on them: k_traverse_line32 (sample_block 8 / 16, refractory >= one
-// chunk), the iid kernel (sample_block 1) or the block kernel (everything else except sample_block 8, which the 64-bit
-// line kernel serves when the refractory period is shorter than a chunk).
+// gate words: slack_mode) and a kernel that works on them: k_traverse_line32 (sample_block 1 / 8 / 16, refractory >= one
+// chunk), the register-staged iid kernel (sample_block 1 otherwise) or the block kernel (everything else except
+// sample_block 8, which the 64-bit line kernel serves when the refractory period is shorter than a chunk).
 static bool line32_kernel(const KParams& kp)
 {
-    return (kp.sample_block == 8 || kp.sample_block == 16) && kp.refractory >= (u64)LINE32_EPC * kp.world;
+    static const bool legacy_iid = tune_env("ABNN_IID_LEGACY") != nullptr;               // A/B measurements only
+    if (kp.sample_block == 1 && legacy_iid) return false;
+    return (kp.sample_block == 1 || kp.sample_block == 8 || kp.sample_block == 16) && kp.refractory >= (u64)LINE32_EPC * kp.world;
 }
 bool line32_selected(const KParams& kp)
 {
@@ -1245,6 +1278,10 @@ cudaError_t launch_traverse_parallel(const KParams& kp, const DevPtrs& d, int sm
         if (kp.sample_block == 16) {
             if (vis) return grow ? launch_line32<1, 1, 16>(kp, d, sm_count, st) : launch_line32<1, 0, 16>(kp, d, sm_count, st);
             return grow ? launch_line32<0, 1, 16>(kp, d, sm_count, st) : launch_line32<0, 0, 16>(kp, d, sm_count, st);
+        }
+        if (kp.sample_block == 1) {
+            if (vis) return grow ? launch_line32<1, 1, 1>(kp, d, sm_count, st) : launch_line32<1, 0, 1>(kp, d, sm_count, st);
+            return grow ? launch_line32<0, 1, 1>(kp, d, sm_count, st) : launch_line32<0, 0, 1>(kp, d, sm_count, st);
         }
         if (vis) return grow ? launch_line32<1, 1, 8>(kp, d, sm_count, st) : launch_line32<1, 0, 8>(kp, d, sm_count, st);
         return grow ? launch_line32<0, 1, 8>(kp, d, sm_count, st) : launch_line32<0, 0, 8>(kp, d, sm_count, st);

@@ -580,7 +580,7 @@ def main():
         wkey = f"{args.hidden}/{args.syn}/{args.events}/{args.sampler}/b{args.block}/{effective_order(args)}/{args.src_view}/w{world}"
         achieved = ev_per_launch * b_alg / (trav_mean * 1e-3) / 1e9
         traffic = ncu_traffic(wkey)
-        line32 = args.sampler == "philox" and args.block in (8, 16) and args.src_view == "snapshot"
+        line32 = args.sampler == "philox" and args.block in (1, 8, 16) and args.src_view == "snapshot"
         line = {
             "metric": "synaptic events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.structural else "strong", "vs_baseline": None,
@@ -630,8 +630,9 @@ def main():
                     subs[name] = sub_record(args, name, peak, **over)
                 except Exception as e:                # a sub-record must never take the headline down
                     subs[name] = {"error": str(e)[:200]}
-            subs["iid_sampler"]["note"] = ("SURVEY §8.0 sampler edge(e) = mulhi(philox(seed,e), N_SYN), table in generation order; bounded by B200's "
-                                           "128-byte DRAM fetch per random 16-byte gather (36.7e9 gathers/s measured, profiles/r1_notes.md §1)")
+            subs["iid_sampler"]["note"] = ("SURVEY §8.0 sampler edge(e) = mulhi(philox(seed,e), N_SYN), table in generation order, on "
+                                           "k_traverse_line32<.,.,1> (one 16-byte cp.async per event); bounded by B200's 128-byte DRAM fetch per "
+                                           "random 16-byte gather (36.7e9 bare gathers/s measured, profiles/r1_notes.md §1)")
             subs["line8_dst_sorted"]["note"] = ("round-1 headline layout: bursts of 8 events per neuron lower the fire rate by a few per cent "
                                                 "(tests/test_gpu_equivalence.py)")
             line["samplers"] = subs

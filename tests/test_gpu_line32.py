@@ -19,7 +19,7 @@ def pair(**over):
     return Brain(p), O.OracleB(p)
 
 
-@pytest.mark.parametrize("block", [8, 16])
+@pytest.mark.parametrize("block", [1, 8, 16])
 def test_single_warp_chains_bit_exact(block):
     """One chunk (224 events <= one chunk of the kernel = one warp) per pass over a dst-sorted table with 64 destinations x 4096 synapses: every
     same-destination dependency of a pass is inside the warp, so PARALLEL must equal the serial oracle bit for bit —
@@ -46,11 +46,12 @@ def test_single_warp_chains_bit_exact(block):
     assert_same_state(b, o, "after growth")
 
 
-@pytest.mark.parametrize("block", [8, 16])
+@pytest.mark.parametrize("block", [1, 8, 16])
 def test_duplicate_lines_in_a_chunk_bit_exact(block):
     """A 64-line table (512 records, 16 destinations x 4 lines): every 256-event chunk draws 32 lines out of 64, so
     most chunks hold the same line twice or more (224-event passes: one chunk). The later copy must see the weights and the fires of the earlier one
-    (the kernel cuts a dense step in front of a repeated line and re-reads the weights): bit-exact over 100 passes."""
+    (the kernel cuts a dense step in front of a repeated line and re-reads the weights): bit-exact over 100 passes.
+    block = 1 is the iid sampler on the same kernel (one 16-byte record per draw): 224 draws out of 512 records."""
     rng = np.random.default_rng(5 + block)
     N, n = 32, 512
     syn = np.zeros(n, O.SYN_DTYPE)
@@ -65,6 +66,38 @@ def test_duplicate_lines_in_a_chunk_bit_exact(block):
         assert_same_stats(sb, so, f"pass {p}")
         fired += so.fired; gated += so.gated
     assert fired > 100 and gated > 500
+    assert_same_state(b, o)
+
+
+def test_iid_sampler_large_table_single_warp_bit_exact():
+    """sample_block = 1 over a table of 2^24 records — the size from which the kernel no longer looks for records drawn
+    twice inside a chunk (probability 1.5e-3 per 224-event pass here, 3e-5 per chunk at 1B records; the seed is chosen so
+    that no pass does — such a pair is two concurrent events on one weight, the race PARALLEL execution has anyway):
+    one chunk per pass, bit-exact against the oracle over 40 passes, table as generated (no order)."""
+    rng = np.random.default_rng(1234)
+    N, n = 256, 1 << 24
+    syn = random_graph(rng, n, N, 0.3, 1.0, dst_lo=16)
+    def draws_a_record_twice(seed):
+        for q in range(40):
+            edges = set()
+            for e in range(q * 224, q * 224 + 224):
+                r = O.philox([e & 0xFFFFFFFF, e >> 32, 0, 0], [seed & 0xFFFFFFFF, seed >> 32])
+                edges.add((((r[0] << 32) | r[1]) * n) >> 64)
+            if len(edges) < 224:
+                return True
+        return False
+    seed = next(s for s in range(42, 60) if not draws_a_record_twice(s))      # 42 repeats record 6483210 in pass 2
+    p = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_PARALLEL, table_order=capi.TABLE_AS_GIVEN, seed=seed,
+                         n_input=16, n_output=16, n_hidden=N - 32, n_syn=n, sample_block=1, window_pre=10**9, refractory=300)
+    b, o = Brain(p), O.OracleB(p)
+    for x in (b, o):
+        x.upload_synapses(syn); x.upload_timestamps(np.full(N, 1, np.uint64), None); x.clock = 1000; x.set_reward(0.1)
+    fired = gated = 0
+    for q in range(40):
+        sb, so = b.run_pass(224), o.run_pass(224)
+        assert_same_stats(sb, so, f"pass {q}")
+        fired += so.fired; gated += so.gated
+    assert fired > 200 and gated > 1000
     assert_same_state(b, o)
 
 

@@ -70,7 +70,11 @@ template <int BL> __global__ void __launch_bounds__(256) k_block_regs(Arrays a, 
 }
 
 // L1..L4: the kernel's structure — 8 warps per CTA, one 4 KB stage per warp, 8 cp.async per lane per chunk
-template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arrays a, u64 n_chunks, unsigned* sink)
+// LEVEL 9 / 10: as 8, with the write-back on a fraction g of the RECORDS (every line gets some: the interleaved table) —
+//   9 into the record's own 16 bytes (array-of-records line: up to 4 dirty sectors per line),
+//  10 into a 32-byte weight sector of the line (records of a line stored field by field: one dirty sector per line).
+// BL = 2: lines drawn in blocks of two (sample_block 16).
+template <int LEVEL, int BL = 1> __global__ void __launch_bounds__(256, 4) k_line_staged(Arrays a, u64 n_chunks, unsigned* sink)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rec = lane & 7, sub = lane >> 3;
@@ -79,7 +83,8 @@ template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arr
     const u64 warps = (u64)gridDim.x * 8, w = (u64)blockIdx.x * 8 + warp;
     unsigned acc = 0;
     for (u64 c = w; c < n_chunks; c += warps) {
-        const u64 my_line = __umul64hi(mix((c * 32 + lane) * 0x9E3779B97F4A7C15ULL + 1), a.n_lines);   // lane L draws line L
+        const u64 my_line = BL == 1 ? __umul64hi(mix((c * 32 + lane) * 0x9E3779B97F4A7C15ULL + 1), a.n_lines)    // lane L draws line L
+                                    : __umul64hi(mix((c * 16 + lane / 2) * 0x9E3779B97F4A7C15ULL + 1), a.n_lines / 2) * 2 + (lane & 1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const u64 line = __shfl_sync(0xffffffffu, my_line, k * 4 + sub);
@@ -103,7 +108,7 @@ template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arr
                 acc += __ldcg(a.fire32 + dst);
                 atomicMax(a.vis32 + dst, (u32)(c * 256 + k * 32 + lane));
             }
-            if (LEVEL == 8) {                                                                 // interleaved order: the 8 records of a line
+            if (LEVEL >= 8) {                                                                 // interleaved order: the 8 records of a line
                 const u32 dst = ((u32)__umul64hi(mix(line), a.n_neuron - 8) & ~7u) + rec;     // target 8 ADJACENT neurons (one sector)
                 acc += __ldcg(a.fire32 + dst);
                 atomicMax(a.vis32 + dst, (u32)(c * 256 + k * 32 + lane));
@@ -117,6 +122,12 @@ template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_line_staged(Arr
                 acc += (unsigned)__ldcg(a.live + dst);
                 atomicMax(a.visited + dst, c * 256 + k * 32 + lane);
             }
+            if (LEVEL >= 9) {
+                if ((u32)mix((line * 8 + rec) ^ (c * 0x5bd1e995u)) < a.g_thresh) {             // a fraction g of the records
+                    if (LEVEL == 9) __stcg(reinterpret_cast<u32*>(a.tab + line * 8 + rec) + 2, r.z + 1u);
+                    else            __stcg(reinterpret_cast<u32*>(a.tab + line * 8) + 16 + rec, r.x);   // (a valid gate index: bytes 64..95 hold records 4 and 5)
+                }
+            } else
             if (LEVEL >= 2 && (u32)mix(line ^ 0x5bd1e995u) < a.g_thresh)                     // a fraction g of the lines is written back
                 __stcg(reinterpret_cast<u32*>(a.tab + line * 8 + rec) + 2, r.z + 1u);
             acc += r.y;
@@ -172,10 +183,17 @@ int main(int argc, char** argv)
     CK(cudaFuncSetAttribute(k_line_staged<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
     CK(cudaFuncSetAttribute(k_line_staged<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608));
+    CK((cudaFuncSetAttribute(k_line_staged<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+    CK((cudaFuncSetAttribute(k_line_staged<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+    CK((cudaFuncSetAttribute(k_line_staged<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+    CK((cudaFuncSetAttribute(k_line_staged<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+    CK((cudaFuncSetAttribute(k_line_staged<10, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+    const bool quick = argc > 4;                              // only the write-pattern rungs (L8 / L9 / L10)
     auto report = [&](const char* name, float ms, double bytes_per_event) {
         printf("%-64s %.3f ms  %6.1f Gev/s  %5.2f TB/s algorithmic\n", name, ms, events / ms / 1e6, events * bytes_per_event / ms / 1e9);
     };
     printf("table %.1f GB (%llu records), %llu neurons, g = %.2f, %d SMs\n", n * 16 / 1e9, n, neurons, g, sm);
+    if (!quick) {
     report("L0 line reads into registers, 2 x 4 lines in flight per warp", timeit([&] { k_line_regs<2><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     report("L0 line reads into registers, 4 x 4 lines in flight per warp", timeit([&] { k_line_regs<4><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     report("L0 line reads into registers, 8 x 4 lines in flight per warp", timeit([&] { k_line_regs<8><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
@@ -183,7 +201,8 @@ int main(int argc, char** argv)
     report("L0b blocks of 4 lines (512 B) per draw", timeit([&] { k_block_regs<4><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     report("L0b blocks of 8 lines (1 KB) per draw", timeit([&] { k_block_regs<8><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
     report("L0b blocks of 32 lines (4 KB) per draw", timeit([&] { k_block_regs<32><<<sm * 8, 256, 0, st>>>(a, n_chunks, sink); }), 16);
-    for (int window = 0; window < 2; ++window) {
+    }
+    for (int window = 0; window < 2 && !quick; ++window) {
         if (window) {                       // persisting window over [gate | visited] = 12 B per neuron, like the product
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, 0);
@@ -241,6 +260,18 @@ int main(int argc, char** argv)
         }
         CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
         const size_t sh = 8 * 4608;
+        if (quick) {
+            if (window != 1) continue;
+            for (int rep = 0; rep < 2; ++rep) {
+            report("L8  write-back: all records of a fraction g of the lines", timeit([&] { k_line_staged<8><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+            report("L9  write-back: a fraction g of the records, in place", timeit([&] { k_line_staged<9><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+            report("L10 write-back: a fraction g of the records, weight sector", timeit([&] { k_line_staged<10><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+            report("L8  blocks of 2 lines", timeit([&] { k_line_staged<8, 2><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+            report("L9  blocks of 2 lines", timeit([&] { k_line_staged<9, 2><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+            report("L10 blocks of 2 lines", timeit([&] { k_line_staged<10, 2><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
+            }
+            continue;
+        }
         report("L3 gate read per record (20 MB array)", timeit([&] { k_line_staged<3><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
         report("L7 + 4-byte read per line of packed dstw (40 MB)", timeit([&] { k_line_staged<7><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
         report("L5 + RED.MAX.32 on the same 8-byte word", timeit([&] { k_line_staged<5><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
