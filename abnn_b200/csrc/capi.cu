@@ -439,22 +439,31 @@ int sort_table(abnn_handle* h)
 // number of existing records that survived.
 // With list == null the m new records are already in h->mg_new (the filtered tail of a periodic rebuild) and n_ordered is
 // the size of the ordered region they are merged into.
+// Scratch for m new records (two copies + sort keys), cached in the handle: cudaMalloc / cudaFree next to a 16 GB table
+// cost more than the merge itself (18 - 78 ms measured), so it is sized by `expect` (what later steps will need) when that
+// is larger and never shrinks.
+static int ensure_merge_scratch(abnn_handle* h, u64 m, u64 expect)
+{
+    if (m <= h->mg_cap) return 0;
+    const u64 want = std::min<u64>(std::max(m, expect), 1ull << 31);
+    cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp);
+    h->mg_new = nullptr; h->mg_keys = nullptr; h->mg_tmp = nullptr; h->mg_cap = 0;
+    const u32 cap_m = next_pow2((u32)want);
+    h->mg_tmp_bytes = sort_by_dst_temp_bytes(cap_m);
+    CU(cudaMalloc(&h->mg_new, 2 * (size_t)cap_m * sizeof(abnn_synapse)));
+    CU(cudaMalloc(&h->mg_keys, 2 * (size_t)cap_m * sizeof(u32)));
+    CU(cudaMalloc(&h->mg_tmp, h->mg_tmp_bytes ? h->mg_tmp_bytes : 16));
+    h->mg_cap = cap_m;
+    return 0;
+}
+
 int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nullptr, u64 n_ordered = ~0ull)
 {
     const u64 n = n_ordered == ~0ull ? h->n_local : n_ordered;
     const u32 span = (u32)(h->hi - h->lo);
-    // scratch for the new records is cached in the handle (cudaMalloc / cudaFree next to a 16 GB table cost more
-    // than the merge itself)
     if (m > h->mg_cap) {
         if (!list) return fail(ABNN_ERR_INVALID, "merge_grown: ready records need the scratch sized beforehand");
-        cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp);
-        h->mg_new = nullptr; h->mg_keys = nullptr; h->mg_tmp = nullptr; h->mg_cap = 0;
-        const u32 cap_m = next_pow2(m);
-        h->mg_tmp_bytes = sort_by_dst_temp_bytes(cap_m);
-        CU(cudaMalloc(&h->mg_new, 2 * (size_t)cap_m * sizeof(abnn_synapse)));
-        CU(cudaMalloc(&h->mg_keys, 2 * (size_t)cap_m * sizeof(u32)));
-        CU(cudaMalloc(&h->mg_tmp, h->mg_tmp_bytes ? h->mg_tmp_bytes : 16));
-        h->mg_cap = cap_m;
+        RET(ensure_merge_scratch(h, m, 2ull * m));
     }
     if (!h->mg_cnt) {
         h->mg_scan_bytes = merge_scan_temp_bytes((u64)span + 2);
@@ -1552,10 +1561,14 @@ int gather_growth(abnn_handle* h, GrowCand** list_out, u32* owned_out, bool othe
         RET(ensure_scratch(h, grow_sort_scratch_bytes(std::max<u32>(next_pow2(total), h->p.world_size > 1 ? h->grow_all_buf : h->grow_buf))));
         CU(cudaMemsetAsync(h->d_total + 1, 0, sizeof(u64), h->st));
         CU(launch_grow_sort_count(list, total, (u32)h->lo, (u32)h->hi, reinterpret_cast<u32*>(h->d_total + 1), h->d_scratch, h->st));
-        u64 owned64 = 0;
-        CU(cudaMemcpyAsync(&owned64, h->d_total + 1, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
-        CU(cudaStreamSynchronize(h->st));
-        *owned_out = (u32)owned64;
+        if (h->p.world_size == 1) {
+            *owned_out = total;                              // one shard owns every neuron: no count to wait for
+        } else {
+            u64 owned64 = 0;
+            CU(cudaMemcpyAsync(&owned64, h->d_total + 1, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            *owned_out = (u32)owned64;
+        }
     }
     *list_out = list;
     return 0;
@@ -1606,7 +1619,9 @@ static int prune_compact(abnn_handle* h, u64* kept_out)
 // (the whole table is swept then, so candidates are not needed), the tail is merged into the ordered region in the stable
 // order the eager mode keeps (DST_SORTED: sorted insertion behind the existing records of each destination; INTERLEAVED:
 // re-derived; AS_GIVEN: the tail already is where it belongs).
-static int lazy_structural_step(abnn_handle* h, abnn_structural_stats* s, GrowCand* list, u32 owned, const DevScalars& sc)
+// One host synchronisation per step that does not rebuild (the count of records that died); the bookkeeping kernel that
+// follows it is stream-ordered and nobody waits for it.
+static int lazy_structural_step(abnn_handle* h, abnn_structural_stats* s, GrowCand* list, u32 owned, const DevScalars& sc, bool grow)
 {
     const bool rebuild = h->struct_steps % h->p.compact_every == 0;
     const bool prune = h->p.w_prune > 0.f;
@@ -1614,12 +1629,16 @@ static int lazy_structural_step(abnn_handle* h, abnn_structural_stats* s, GrowCa
     u64 marked = 0;
     if (prune && !rebuild) {
         CU(launch_mark_dead(h->d.prune_list, std::min(sc.prune_count, PRUNE_CAP_DEFAULT), h->d_syn, h->p.w_prune, h->d_total + 2, h->st));
-        CU(cudaMemcpyAsync(&marked, h->d_total + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(h->h_pin, h->d_total + 2, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
     }
     // 2. the grown synapses join the tail, in tick order, as many as fit
     const u32 m = (u32)std::min<u64>(owned, h->cap - h->n_local);
     if (m) CU(launch_grow_append(list, m, h->d_syn, h->n_local, h->p.w_init, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    if (grow) { k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc); CU(cudaGetLastError()); }
+    if (prune && !rebuild) {
+        CU(cudaStreamSynchronize(h->st));
+        std::memcpy(&marked, h->h_pin, sizeof(u64));
+    }
     const u64 slots = h->n_local + m;                // table slots before any rebuild
     h->n_local = slots;
     s->appended = m; s->dropped = owned - m;
@@ -1631,16 +1650,8 @@ static int lazy_structural_step(abnn_handle* h, abnn_structural_stats* s, GrowCa
         const u64 tail = slots - h->n_sorted;
         if (h->p.table_order == ABNN_TABLE_DST_SORTED && prune && tail && tail < (1ull << 31) && h->n_sorted) {
             // the tail's survivors become the "new records" of the fused prune + sorted-insertion sweep of the ordered region
-            const u32 cap_m = next_pow2((u32)tail);
-            if (cap_m > h->mg_cap) {
-                cudaFree(h->mg_new); cudaFree(h->mg_keys); cudaFree(h->mg_tmp);
-                h->mg_new = nullptr; h->mg_keys = nullptr; h->mg_tmp = nullptr; h->mg_cap = 0;
-                h->mg_tmp_bytes = sort_by_dst_temp_bytes(cap_m);
-                CU(cudaMalloc(&h->mg_new, 2 * (size_t)cap_m * sizeof(abnn_synapse)));
-                CU(cudaMalloc(&h->mg_keys, 2 * (size_t)cap_m * sizeof(u32)));
-                CU(cudaMalloc(&h->mg_tmp, h->mg_tmp_bytes ? h->mg_tmp_bytes : 16));
-                h->mg_cap = cap_m;
-            }
+            // the first rebuild (step 0) sees one step's growth, the later ones compact_every steps' worth
+            RET(ensure_merge_scratch(h, tail, std::min<u64>(2 * tail * (h->struct_steps ? 1 : h->p.compact_every), h->cap - h->n_sorted)));
             CompactArgs a{};
             a.in = h->d_syn + h->n_sorted; a.out = h->mg_new; a.n = tail; a.pred = KEEP_NOT_PRUNED; a.w_prune = h->p.w_prune; a.out_cap = h->mg_cap;
             RET(ensure_scratch(h, std::max(compact_scratch_bytes(h->cap), compact2_scratch_bytes(h->cap))));
@@ -1689,7 +1700,7 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
         return fail(ABNN_ERR_CAPACITY, "prune staging buffer overflowed; call abnn_prune_and_grow more often");
     }
     if (lazy) {
-        RET(lazy_structural_step(h, &s, list, owned, sc));
+        RET(lazy_structural_step(h, &s, list, owned, sc, grow));
     } else if (prune && owned && h->p.table_order == ABNN_TABLE_DST_SORTED && !resort && !no_fuse && owned <= h->cap - h->n_local) {
         // 1+2 fused: one pass over the table removes the pruned records and opens the slots of the new ones
         u64 kept = 0;
@@ -1719,12 +1730,14 @@ int abnn_prune_and_grow(abnn_handle* h, abnn_structural_stats* out)
             s.appended = m; s.dropped = owned - m;
         }
     }
-    if (grow) {
-        k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
-        CU(cudaGetLastError());
+    if (!lazy) {
+        if (grow) {
+            k_reset_grow<<<1, 1, 0, h->st>>>(h->d.sc);
+            CU(cudaGetLastError());
+        }
+        CU(cudaStreamSynchronize(h->st));
+        h->n_sorted = h->n_local;
     }
-    CU(cudaStreamSynchronize(h->st));
-    if (!lazy) { h->n_sorted = h->n_local; }
     s.n_after = h->n_local;
     h->counts_dirty = true;
     if (h->p.world_size == 1) h->n_local_all.assign(1, h->n_local);

@@ -69,7 +69,7 @@ def parse():
     ap.add_argument("--no-visits", action="store_true")
     ap.add_argument("--no-l2-persist", action="store_true")
     ap.add_argument("--structural", action="store_true", help="BASELINE configs[4]: prune + grow after every pass")
-    ap.add_argument("--compact-every", type=int, default=16,
+    ap.add_argument("--compact-every", type=int, default=64,
                     help="--structural: abnn_params.compact_every (1 = rebuild the table at every structural step; K > 1 = mark dead in "
                          "place + append behind the table, rebuild every K-th step: README.md:122-124 'compact periodically')")
     ap.add_argument("--cpu-syn", type=int, default=0, help="table of the CPU arm (default: the GPU arm's when the host has the memory, else 1e8)")
@@ -617,7 +617,10 @@ def main():
                                   # stable compaction + sorted insertion out of place: 16 B read (count) + 16 B read + 16 B written per record
                                   "sweep_roofline_frac": ((48.0 * n_after / world) / (struct_mean * 1e-3) / 1e9 / peak
                                                           if struct_mean and args.compact_every <= 1 else None),
-                                  "note": "ms_per_step includes the structural step (the device timer spans the synchronising abnn_prune_and_grow)"}
+                                  # the host-timed call starts while the pass is still running on the device: without the traversal
+                                  "ms_per_structural_step_excl_traversal": struct_mean - trav_mean,
+                                  "note": "ms_per_step includes the structural step (the device timer spans the synchronising abnn_prune_and_grow); "
+                                          "use --steps >= 2 * compact_every so that the timed region holds its share of rebuild steps"}
         if parity is not None:
             line["parity"] = parity
         if world == 1 and not args.skip_variants and not args.structural:
