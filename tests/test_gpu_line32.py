@@ -134,13 +134,13 @@ def test_interleaved_table_single_warp_bit_exact(block):
 
 
 def test_ragged_table_and_passes_visits_exact():
-    """Table length not a multiple of the line or the 16-record block, passes of 1, 7, 255, 257, 4099 events, per-event
+    """Table length not a multiple of the line or the 16-record block (sample_block 1, 8, 16), passes of 1, 7, 223, 257, 4099 events, per-event
     ticks that need the ANCIENT sentinel (clock far beyond 2^30 past the last fires): lastVisited and the candidate
     count are order-free and must equal the oracle's exactly; single-warp passes are bit-exact as a whole."""
     rng = np.random.default_rng(8)
     N, n = 300, 4099
     syn = random_graph(rng, n, N, 0.4, 1.0, dst_lo=8)
-    for block in (8, 16):
+    for block in (1, 8, 16):
         b, o = pair(n_input=4, n_output=4, n_hidden=N - 8, n_syn=n, sample_block=block, window_pre=10**12, refractory=1000)
         pre = rng.integers(1, 50, N).astype(np.uint64)
         for x in (b, o):
@@ -178,9 +178,9 @@ def test_future_source_timestamps_take_the_exact_gate():
 
 
 def test_statistical_parity_and_visits_at_2m_synapses():
-    """Many warps in flight (2M synapses, 700k-event passes, sample_block 8 and 16): lastVisited and the first pass's
+    """Many warps in flight (2M synapses, 700k-event passes, sample_block 1, 8 and 16): lastVisited and the first pass's
     candidates equal the oracle's exactly; gated / fired counts within 2 % + 5 sigma (refractory period = 0.7 pass)."""
-    for block in (8, 16):
+    for block in (1, 8, 16):
         b, o = pair(n_input=64, n_output=64, n_hidden=200_000, n_syn=2_000_003, sample_block=block,
                     window_pre=3_000_000, refractory=500_000)
         b.init_graph(capi.GRAPH_ER_BETA, 5); o.init_graph(capi.GRAPH_ER_BETA, 5)
