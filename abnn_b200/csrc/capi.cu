@@ -105,7 +105,7 @@ struct abnn_handle {
     void* peer_ts[P2P_MAX_WORLD]{}; void* peer_flags[P2P_MAX_WORLD]{};
     P2PTable p2p_tab{};
     // EXACT execution scratch (allocated on first use)
-    u64* d_xkeys = nullptr; u64* d_xvals = nullptr; u32* d_xcount = nullptr; void* d_xtmp = nullptr;
+    u64* d_xkeys = nullptr; u32* d_xbucket = nullptr; u32* d_xcnt = nullptr; u32* d_xcount = nullptr; void* d_xtmp = nullptr;
     u64 x_cap = 0; size_t x_tmp_bytes = 0;
     bool timing = false;
     // sharded PARALLEL runs exchange the 32-bit slack slices instead of the 64-bit lastFired slices:
@@ -510,23 +510,26 @@ int merge_grown(abnn_handle* h, const GrowCand* list, u32 m, u64* kept_out = nul
     return 0;
 }
 
-// EXACT execution: phase 1 (candidates) -> radix sort by (dst, event) -> phase 3 (per-destination chains).
-// The candidate count never leaves the device: the key buffer is padded to its capacity (= the events of the pass) with a
-// key that sorts behind every neuron, the sort always runs over the whole buffer, and phase 3 reads the count from device
-// memory — no host synchronisation inside a pass, so an EXACT pass can be enqueued asynchronously and captured into a
-// CUDA graph like a PARALLEL one. (Cost: a pass with few candidates still sorts `events` keys.)
+// EXACT execution: phase 1 (open events, counted per destination) -> scan + scatter into per-destination buckets ->
+// phase 3 (per-destination chains). No count leaves the device: the buffers are sized by the events of the pass and the
+// kernels read the counts from device memory — no host synchronisation inside a pass, so an EXACT pass can be enqueued
+// asynchronously and captured into a CUDA graph like a PARALLEL one.
 int ensure_exact_scratch(abnn_handle* h, const KParams& kp)
 {
     if (kp.count >= (1ull << 32)) return fail(ABNN_ERR_UNSUPPORTED, "EXACT execution: at most 2^32-1 events per rank per pass");
-    if (kp.count > h->x_cap) {
-        cudaFree(h->d_xkeys); cudaFree(h->d_xvals); cudaFree(h->d_xtmp);
-        h->d_xkeys = h->d_xvals = nullptr; h->d_xtmp = nullptr; h->x_cap = 0;
-        const u64 cap = kp.count;
-        CU(cudaMalloc(&h->d_xkeys, 2 * cap * sizeof(u64)));
-        CU(cudaMalloc(&h->d_xvals, 2 * cap * sizeof(u64)));
-        h->x_tmp_bytes = exact_sort_temp_bytes(cap);
+    const u64 span = h->hi - h->lo;
+    if (!h->d_xcnt) {
+        CU(cudaMalloc(&h->d_xcnt, 2 * std::max<u64>(span, 1) * sizeof(u32)));            // counts, then cursors
+        CU(cudaMalloc(&h->d_xcount, 2 * sizeof(u32)));
+        h->x_tmp_bytes = exact_scan_temp_bytes(span);
         CU(cudaMalloc(&h->d_xtmp, h->x_tmp_bytes ? h->x_tmp_bytes : 16));
-        if (!h->d_xcount) CU(cudaMalloc(&h->d_xcount, sizeof(u32)));
+    }
+    if (kp.count > h->x_cap) {
+        cudaFree(h->d_xkeys); cudaFree(h->d_xbucket);
+        h->d_xkeys = nullptr; h->d_xbucket = nullptr; h->x_cap = 0;
+        const u64 cap = kp.count;
+        CU(cudaMalloc(&h->d_xkeys, cap * sizeof(u64)));
+        CU(cudaMalloc(&h->d_xbucket, cap * sizeof(u32)));
         h->x_cap = cap;
         if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old buffers
     }
@@ -536,10 +539,11 @@ int run_exact(abnn_handle* h, const KParams& kp)
 {
     RET(ensure_exact_scratch(h, kp));                 // no-op once the buffers fit (abnn_engine_step sizes them before a capture)
     if (!kp.count) return 0;
-    int nb = 1; while ((1ull << nb) < h->N) ++nb;     // bits of a neuron id; the pad key's destination is 1 << nb
-    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, h->d_xvals, h->d_xcount, kp.count, nb, h->sm_count, h->st));
-    CU(launch_exact_sort(h->d_xkeys, h->d_xvals, h->x_cap, (u32)kp.count, 32 + nb + 1, h->d_xtmp, h->x_tmp_bytes, h->st));
-    CU(launch_exact_phase3(kp, h->d, h->d_xkeys + h->x_cap, h->d_xvals + h->x_cap, h->d_xcount, (u32)kp.count, h->sm_count, h->st));
+    const u32 lo = (u32)h->lo, span = (u32)(h->hi - h->lo);
+    u32 *cnt = h->d_xcnt, *cursor = h->d_xcnt + std::max<u64>(span, 1);
+    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, cnt, lo, span, h->d_xcount, h->sm_count, h->st));
+    CU(launch_exact_group(h->d_xkeys, h->d_xcount, cnt, cursor, lo, span, h->d_xbucket, h->d_xtmp, h->x_tmp_bytes, h->sm_count, h->st));
+    CU(launch_exact_phase3(kp, h->d, h->d_xbucket, cnt, cursor, lo, span, h->d_xcount, h->sm_count, h->st));
     return 0;
 }
 
@@ -799,7 +803,7 @@ void abnn_destroy(abnn_handle* h)
     if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
     cudaFree(h->d_frame); cudaFreeHost(h->h_frame);
     for (int i = 0; i < RING; ++i) if (h->frame_ev[i]) cudaEventDestroy(h->frame_ev[i]);
-    cudaFree(h->d_xkeys); cudaFree(h->d_xvals); cudaFree(h->d_xcount); cudaFree(h->d_xtmp);
+    cudaFree(h->d_xkeys); cudaFree(h->d_xbucket); cudaFree(h->d_xcnt); cudaFree(h->d_xcount); cudaFree(h->d_xtmp);
     for (int i = 0; i < RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
