@@ -227,7 +227,7 @@ typedef struct abnn_pass_stats {
     uint64_t events;        /* events this rank executed in the pass                            */
     uint64_t gated;         /* events that passed window + refractory + budget gates (weight written) */
     uint64_t fired;         /* events that fired (timestamp written)                            */
-    uint64_t candidates;    /* events that passed the src window (EXACT mode phase-2 list)      */
+    uint64_t candidates;    /* events that passed the src (pre-spike) window                      */
     uint64_t grown;         /* synaptogenesis candidates staged this pass                       */
     uint64_t clock;         /* clock after the pass                                             */
     double   device_ms;     /* device time of the pass (CUDA events), incl. timestamp exchange  */

@@ -361,7 +361,7 @@ def test_engine_step_graph_replay_is_bit_exact():
 
 
 def test_engine_step_exact_mode_is_captured_and_bit_exact():
-    """EXACT execution keeps its candidate count on the device (padded sort), so abnn_engine_step records it into a CUDA
+    """EXACT execution keeps its event counts on the device (buffers sized by the events of the pass), so abnn_engine_step records it into a CUDA
     graph like a PARALLEL pass: line sampler over the interleaved table, conflicts and growth on, 8 engine steps — every
     filtered read-out and the final state equal the oracle bit for bit."""
     over = dict(n_input=64, n_output=64, n_hidden=3000, n_syn=120_000, exec_mode=capi.EXEC_EXACT, sample_block=8,
