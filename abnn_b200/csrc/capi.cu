@@ -529,7 +529,7 @@ int ensure_exact_scratch(abnn_handle* h, const KParams& kp)
         h->d_xkeys = nullptr; h->d_xbucket = nullptr; h->x_cap = 0;
         const u64 cap = kp.count;
         CU(cudaMalloc(&h->d_xkeys, cap * sizeof(u64)));
-        CU(cudaMalloc(&h->d_xbucket, cap * sizeof(u32)));
+        CU(cudaMalloc(&h->d_xbucket, 2 * cap * sizeof(u32)));                            // buckets, then arrival numbers
         h->x_cap = cap;
         if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }   // the captured pass holds the old buffers
     }
@@ -541,8 +541,9 @@ int run_exact(abnn_handle* h, const KParams& kp)
     if (!kp.count) return 0;
     const u32 lo = (u32)h->lo, span = (u32)(h->hi - h->lo);
     u32 *cnt = h->d_xcnt, *cursor = h->d_xcnt + std::max<u64>(span, 1);
-    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, cnt, lo, span, h->d_xcount, h->sm_count, h->st));
-    CU(launch_exact_group(h->d_xkeys, h->d_xcount, cnt, cursor, lo, span, h->d_xbucket, h->d_xtmp, h->x_tmp_bytes, h->sm_count, h->st));
+    u32* slot = h->d_xbucket + h->x_cap;
+    CU(launch_exact_phase1(kp, h->d, h->d_xkeys, slot, cnt, lo, span, h->d_xcount, h->sm_count, h->st));
+    CU(launch_exact_group(h->d_xkeys, slot, h->d_xcount, cnt, cursor, lo, span, h->d_xbucket, h->d_xtmp, h->x_tmp_bytes, h->sm_count, h->st));
     CU(launch_exact_phase3(kp, h->d, h->d_xbucket, cnt, cursor, lo, span, h->d_xcount, h->sm_count, h->st));
     return 0;
 }

@@ -9,7 +9,8 @@
 //                                          lastFired[dst] AS IT IS AT THE START OF THE PASS; survivors are
 //                                          emitted as (dst << 32 | event index) and counted per destination;
 //   group    (scan + scatter)            : exclusive scan of the per-destination counts, then every survivor's
-//                                          event index goes into its destination's bucket (a counting sort by
+//                                          event index goes into its destination's bucket, at the arrival number
+//                                          the counting atomic of phase 1 returned (a counting sort by
 //                                          destination: one pass over the survivors instead of a 7-pass radix
 //                                          sort of a buffer padded to the events of the pass);
 //   phase 3  (parallel over destinations): one thread per destination sorts its bucket by event index (a few
@@ -50,10 +51,11 @@ __device__ __forceinline__ bool sample_edge(const KParams& kp, u64 event_base, u
 
 // list[0 .. counter[0]) = (dst << 32 | event) of the events still open against the pass-start lastFired, in no particular
 // order (one slot reservation per CTA and round, not per warp: 600k atomics on one address instead of 4.7M);
-// cnt[dst - lo] = how many of them each destination got; counter[1] = events that passed the pre-spike window (the
-// pass's candidate count)
-__global__ void __launch_bounds__(256) k_exact_phase1(const __grid_constant__ KParams kp, const DevPtrs d, u64* list, u32* cnt, u32 lo,
-                                                      u32* counter)
+// cnt[dst - lo] = how many of them each destination got, slot[j] = the arrival number of list[j] at its destination (the
+// value the counting atomic returned: the scatter needs no second round of atomics); counter[1] = events that passed the
+// pre-spike window (the pass's candidate count)
+__global__ void __launch_bounds__(256) k_exact_phase1(const __grid_constant__ KParams kp, const DevPtrs d, u64* list, u32* slot, u32* cnt,
+                                                      u32 lo, u32* counter)
 {
     __shared__ u32 s_warp[8], s_base;
     const u64 clock = d.sc->clock, event_base = d.sc->event_base;
@@ -90,8 +92,9 @@ __global__ void __launch_bounds__(256) k_exact_phase1(const __grid_constant__ KP
         }
         __syncthreads();
         if (open) {
-            list[s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u))] = ((u64)dst << 32) | (u32)i;
-            atomicAdd(cnt + (dst - lo), 1u);
+            const u32 at = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+            list[at] = ((u64)dst << 32) | (u32)i;
+            slot[at] = atomicAdd(cnt + (dst - lo), 1u);
         }
         __syncthreads();                                     // s_warp / s_base are rewritten in the next round
     }
@@ -99,15 +102,49 @@ __global__ void __launch_bounds__(256) k_exact_phase1(const __grid_constant__ KP
     if (lane == 0 && n_cand) atomicAdd(counter + 1, n_cand);
 }
 
-// cursor[] = exclusive scan of cnt[] on entry; every open event takes the next slot of its destination's bucket, so that
-// cursor[n] ends at the END of bucket n (phase 3 finds the start as cursor[n] - cnt[n])
-__global__ void __launch_bounds__(256) k_exact_scatter(const u64* __restrict__ list, const u32* __restrict__ counter, u32* cursor, u32 lo,
-                                                       u32* bucket)
+// start[] = exclusive scan of cnt[]: bucket n is bucket[start[n] .. start[n] + cnt[n]); every open event goes to the slot of
+// its arrival number
+__global__ void __launch_bounds__(256) k_exact_scatter(const u64* __restrict__ list, const u32* __restrict__ slot,
+                                                       const u32* __restrict__ counter, const u32* __restrict__ start, u32 lo, u32* bucket)
 {
     const u32 n = *counter;
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (u64)gridDim.x * blockDim.x) {
         const u64 it = list[j];
-        bucket[atomicAdd(cursor + ((u32)(it >> 32) - lo), 1u)] = (u32)it;
+        bucket[__ldg(start + ((u32)(it >> 32) - lo)) + slot[j]] = (u32)it;
+    }
+}
+
+// Event order inside a bucket. Buckets hold a few dozen entries in the regimes the kernel is built for (insertion sort);
+// a tiny network under a long pass can put thousands of events on one destination, so larger buckets take a heap sort
+// (in place, O(k log k) whatever the arrival order).
+__device__ __forceinline__ void sift_down(u32* a, u32 root, u32 n)
+{
+    const u32 v = a[root];
+    for (;;) {
+        u32 child = 2 * root + 1;
+        if (child >= n) break;
+        if (child + 1 < n && a[child + 1] > a[child]) ++child;
+        if (a[child] <= v) break;
+        a[root] = a[child];
+        root = child;
+    }
+    a[root] = v;
+}
+__device__ void sort_bucket(u32* bk, u32 k)
+{
+    if (k <= 32) {
+        for (u32 a = 1; a < k; ++a) {
+            const u32 v = bk[a];
+            u32 b = a;
+            while (b > 0 && bk[b - 1] > v) { bk[b] = bk[b - 1]; --b; }
+            bk[b] = v;
+        }
+        return;
+    }
+    for (u32 start = k / 2; start-- > 0;) sift_down(bk, start, k);
+    for (u32 end = k - 1; end > 0; --end) {
+        const u32 top = bk[0]; bk[0] = bk[end]; bk[end] = top;
+        sift_down(bk, 0, end);
     }
 }
 
@@ -125,13 +162,8 @@ __global__ void __launch_bounds__(256) k_exact_phase3(const __grid_constant__ KP
         const u32 k = cnt[nn];
         if (!k) continue;
         const u32 dst = lo + (u32)nn;
-        u32* bk = bucket + (cursor[nn] - k);
-        for (u32 a = 1; a < k; ++a) {                        // event order inside the bucket (insertion sort: a few dozen entries)
-            const u32 v = bk[a];
-            u32 b = a;
-            while (b > 0 && bk[b - 1] > v) { bk[b] = bk[b - 1]; --b; }
-            bk[b] = v;
-        }
+        u32* bk = bucket + cursor[nn];
+        sort_bucket(bk, k);
         u64 ld = d.live[dst];
         const u64 ld0 = ld;
         for (u32 t = 0; t < k; ++t) {
@@ -198,9 +230,9 @@ size_t exact_scan_temp_bytes(u64 span)
     return bytes;
 }
 
-// list: cap entries; bucket: cap entries; cnt / cursor: span entries each; counter: two words (k_exact_phase1)
-cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* list, u32* cnt, u32 lo, u32 span, u32* counter, int sm_count,
-                                cudaStream_t st)
+// list / slot / bucket: cap entries each; cnt / cursor: span entries each; counter: two words (k_exact_phase1)
+cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* list, u32* slot, u32* cnt, u32 lo, u32 span, u32* counter,
+                                int sm_count, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(counter, 0, 2 * sizeof(u32), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, (size_t)span * sizeof(u32), st);
@@ -208,15 +240,15 @@ cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* list, 
     u64 blocks = (kp.count + 255) / 256;
     const u64 cap = (u64)sm_count * 8;
     if (blocks > cap) blocks = cap;
-    k_exact_phase1<<<(unsigned)blocks, 256, 0, st>>>(kp, d, list, cnt, lo, counter);
+    k_exact_phase1<<<(unsigned)blocks, 256, 0, st>>>(kp, d, list, slot, cnt, lo, counter);
     return cudaGetLastError();
 }
-cudaError_t launch_exact_group(const u64* list, const u32* counter, const u32* cnt, u32* cursor, u32 lo, u32 span, u32* bucket, void* tmp,
-                               size_t tmp_bytes, int sm_count, cudaStream_t st)
+cudaError_t launch_exact_group(const u64* list, const u32* slot, const u32* counter, const u32* cnt, u32* cursor, u32 lo, u32 span,
+                               u32* bucket, void* tmp, size_t tmp_bytes, int sm_count, cudaStream_t st)
 {
     cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, cursor, (size_t)span, st);
     if (e != cudaSuccess) return e;
-    k_exact_scatter<<<(unsigned)sm_count * 8, 256, 0, st>>>(list, counter, cursor, lo, bucket);
+    k_exact_scatter<<<(unsigned)sm_count * 8, 256, 0, st>>>(list, slot, counter, cursor, lo, bucket);
     return cudaGetLastError();
 }
 cudaError_t launch_exact_phase3(const KParams& kp, const DevPtrs& d, u32* bucket, const u32* cnt, const u32* cursor, u32 lo, u32 span,

@@ -37,11 +37,12 @@ cudaError_t launch_p2p_exchange(const KParams& kp, const DevPtrs& d, const P2PTa
 size_t exact_scan_temp_bytes(u64 span);
 // events still open against the pass-start lastFired into list[0 .. counter[0]) as (dst << 32 | event), counted per destination in
 // cnt[dst - lo]; counter[1] = events that passed the pre-spike window
-cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* list, u32* cnt, u32 lo, u32 span, u32* counter, int sm_count,
-                                cudaStream_t st);
-// cursor = exclusive scan of cnt, then bucket[] = the event indices grouped by destination (cursor[n] ends behind bucket n)
-cudaError_t launch_exact_group(const u64* list, const u32* counter, const u32* cnt, u32* cursor, u32 lo, u32 span, u32* bucket, void* tmp,
-                               size_t tmp_bytes, int sm_count, cudaStream_t st);
+// (slot[j] = arrival number of list[j] at its destination)
+cudaError_t launch_exact_phase1(const KParams& kp, const DevPtrs& d, u64* list, u32* slot, u32* cnt, u32 lo, u32 span, u32* counter,
+                                int sm_count, cudaStream_t st);
+// cursor = exclusive scan of cnt, then bucket[cursor[n] + slot] = the event indices grouped by destination
+cudaError_t launch_exact_group(const u64* list, const u32* slot, const u32* counter, const u32* cnt, u32* cursor, u32 lo, u32 span,
+                               u32* bucket, void* tmp, size_t tmp_bytes, int sm_count, cudaStream_t st);
 cudaError_t launch_exact_phase3(const KParams& kp, const DevPtrs& d, u32* bucket, const u32* cnt, const u32* cursor, u32 lo, u32 span,
                                 const u32* counter, int sm_count, cudaStream_t st);
 

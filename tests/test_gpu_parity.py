@@ -206,6 +206,24 @@ def test_exact_mode_er_graph_many_conflicts():
     assert_same_state(b, o, "after growth")
 
 
+def test_exact_mode_tiny_network_thousands_of_events_per_destination():
+    """24 neurons under 60,000-event passes with a refractory period of 2 ticks: every destination collects thousands of
+    open events per pass (phase 3 sorts its bucket with the heap-sort path) and walks them all; block and iid sampler."""
+    rng = np.random.default_rng(77)
+    N, n = 24, 4096
+    syn = random_graph(rng, n, N, 0.05, 1.0, dst_lo=4)
+    for block in (1, 16):
+        b, o = pair(capi.PROFILE_NORTH_STAR, n_input=4, n_output=4, n_hidden=N - 8, n_syn=n, exec_mode=capi.EXEC_EXACT,
+                    sample_block=block, window_pre=10**9, refractory=2)
+        for x in (b, o):
+            x.upload_synapses(syn); x.upload_timestamps(np.full(N, 1, np.uint64), None); x.clock = 1000; x.set_reward(0.3)
+        for p in range(2):
+            sb, so = b.run_pass(60_000), o.run_pass(60_000)
+            assert_same_stats(sb, so, f"block {block} pass {p}")
+            assert so.gated > 30_000 and so.fired > 1000
+        assert_same_state(b, o, f"block {block}")
+
+
 # ---- dst-sorted table layout (ABNN_TABLE_DST_SORTED) ----------------------------------------------------
 @pytest.mark.parametrize("mode", [capi.EXEC_SERIAL, capi.EXEC_EXACT])
 def test_dst_sorted_table_bit_exact(mode):
