@@ -754,6 +754,12 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
 #ifndef ABNN_LINE_STEPS
 #define ABNN_LINE_STEPS 8
 #endif
+// ABNN_LINE_TMA=1 (measurement builds): the stage is filled by cp.async.bulk — lane L issues ONE bulk copy of its whole
+// 128-byte line, completion on a per-warp mbarrier — instead of 8 LDGSTS.128 per lane. Measured slower (profiles/r2_notes.md
+// §9), kept as the evidence for the choice.
+#ifndef ABNN_LINE_TMA
+#define ABNN_LINE_TMA 0
+#endif
 constexpr u32 LINE32_CQ = ABNN_LINE_CQ;                    // 0: no compacted copy — the dense steps read the stage in place
 constexpr bool LINE32_EARLY = LINE32_CQ > 0 && ABNN_LINE_EARLY;
 constexpr int LINE32_STEPS = ABNN_LINE_STEPS;              // steps of 4 lines per chunk: a chunk is 4 * STEPS lines
@@ -771,9 +777,20 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
     static_assert(SB == 1 || SB == 8 || SB == 16, "line kernel: sample_block 1, 8 or 16");
     extern __shared__ __align__(128) unsigned char line_smem[];
     __shared__ u32 s_cnt[3];
+#if ABNN_LINE_TMA
+    __shared__ __align__(8) u64 s_mbar[LINE_WARPS];
+#endif
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NS = LINE32_STEPS;
     unsigned char* stage = line_smem + warp * LINE32_WARP_SMEM;
+#if ABNN_LINE_TMA
+    const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar[warp]);
+    u32 tma_phase = 0;
+    bool tma_pending = false;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+#endif
     uint4* cq = reinterpret_cast<uint4*>(stage + LINE32_STAGE);                // open events of the chunk: src, dst, w, fire word
     unsigned char* queue = stage + LINE32_STAGE + LINE32_CQ * 16;              // their chunk-local event indices
     u32* fl_dst = reinterpret_cast<u32*>(queue + 256);             // destinations that fired in this chunk
@@ -835,6 +852,30 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
             cp_async_commit();
             return ok;
         }
+#if ABNN_LINE_TMA
+        if (!IID) {
+            // lane L copies line L (stage + L * 128) in one bulk operation; the warp's mbarrier counts the bytes
+            const bool have = lane < LINE32_LPC && (u32)(mm >> 32) != 0xFFFFFFFFu;
+            const u32 bytes = have ? (((u32)mm & 7u) + 1u) * 16u : 0u;
+            const u32 total = __reduce_add_sync(0xffffffffu, bytes);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const u64 mk = __shfl_sync(0xffffffffu, mm, k * 4 + sub);
+                if ((u32)(mk >> 32) != 0xFFFFFFFFu && rec <= ((u32)mk & 7u)) ok |= 1u << k;
+            }
+            tma_pending = total != 0;
+            if (total) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the stage was read / written through the generic proxy
+                if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
+                __syncwarp();
+                if (have)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((u32)__cvta_generic_to_shared(stage + lane * 128)), "l"(d.syn + (mm & ~7ull)), "r"(bytes), "r"(mbar)
+                                 : "memory");
+            }
+            return ok;
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const u64 mk = __shfl_sync(0xffffffffu, mm, k * 4 + sub);
@@ -866,6 +907,17 @@ __global__ void __launch_bounds__(LINE_WARPS * 32, ABNN_LINE_MIN_CTAS) k_travers
         const u64 m_next = draw(c_next, zw_next);            // ALU work under the copy's latency
         const u32 ev0 = c * LINE32_EPC;                      // first event of the chunk (local index)
         const u32 t0 = ev0 * world + kp.rank;                // its tick offset: now = clock + t
+#if ABNN_LINE_TMA
+        if (!IID) {
+            if (tma_pending) {
+                u32 done = 0;
+                while (!done)
+                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                                 : "=r"(done) : "r"(mbar), "r"(tma_phase), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
+                tma_phase ^= 1u;
+            }
+        } else
+#endif
         cp_async_wait<0>();
         __syncwarp();
 
