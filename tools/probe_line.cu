@@ -137,6 +137,45 @@ template <int LEVEL, int BL = 1> __global__ void __launch_bounds__(256, 4) k_lin
     if (acc == 0x12345678u) *sink = acc;
 }
 
+// I0..I3: the iid sampler's streams (k_traverse_line32<.,.,1>): every EVENT gathers its own random 16-byte record with cp.async
+// (256 per warp and chunk); LEVEL 1 + one gate read per record, 2 + fire32 read and vis32 RED per record, 3 + 4-byte
+// write-back on a fraction g of the records
+template <int LEVEL> __global__ void __launch_bounds__(256, 4) k_iid_staged(Arrays a, u64 n_chunks, unsigned* sink)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = smem + warp * 4096;
+    const u32 mine = (u32)__cvta_generic_to_shared(stage + lane * 16);
+    const u64 warps = (u64)gridDim.x * 8, w = (u64)blockIdx.x * 8 + warp, n_rec = a.n_lines * 8;
+    unsigned acc = 0;
+    for (u64 c = w; c < n_chunks; c += warps) {
+        u64 recs[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            recs[k] = __umul64hi(mix((c * 256 + k * 32 + lane) * 0x9E3779B97F4A7C15ULL + 1), n_rec);
+            cp_async16(mine + k * 512, a.tab + recs[k]);
+        }
+        cp_async_commit();
+        cp_async_wait0();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 r = *reinterpret_cast<const uint4*>(stage + lane * 16 + k * 512);
+            if (LEVEL >= 1) acc += __ldcg(a.gate + r.x);
+            if (LEVEL >= 2) {
+                const u32 dst = (u32)__umul64hi(mix(recs[k]), a.n_neuron);
+                acc += __ldcg(a.fire32 + dst);
+                atomicMax(a.vis32 + dst, (u32)(c * 256 + k * 32 + lane));
+            }
+            if (LEVEL >= 3 && (u32)mix(recs[k] ^ (c * 0x5bd1e995u)) < a.g_thresh)
+                __stcg(reinterpret_cast<u32*>(a.tab + recs[k]) + 2, r.z + 1u);
+            acc += r.y;
+        }
+        __syncwarp();
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
 // table records: x = uniformly random source neuron (the gate-word index), y = z = w = filler
 __global__ void k_init_table(uint4* tab, u64 n, u64 n_neuron)
 {
@@ -262,6 +301,14 @@ int main(int argc, char** argv)
         const size_t sh = 8 * 4608;
         if (quick) {
             if (window != 1) continue;
+            CK((cudaFuncSetAttribute(k_iid_staged<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+            CK((cudaFuncSetAttribute(k_iid_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+            CK((cudaFuncSetAttribute(k_iid_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+            CK((cudaFuncSetAttribute(k_iid_staged<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4608)));
+            report("I0 iid: one random 16-byte record per event (cp.async, 256 per warp)", timeit([&] { k_iid_staged<0><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16);
+            report("I1 + gate read per record", timeit([&] { k_iid_staged<1><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16);
+            report("I2 + fire32 read and vis32 RED per record", timeit([&] { k_iid_staged<2><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16);
+            report("I3 + 4-byte write-back on a fraction g of the records", timeit([&] { k_iid_staged<3><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
             for (int rep = 0; rep < 2; ++rep) {
             report("L8  write-back: all records of a fraction g of the lines", timeit([&] { k_line_staged<8><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
             report("L9  write-back: a fraction g of the records, in place", timeit([&] { k_line_staged<9><<<sm * 4, 256, sh, st>>>(b, n_chunks, sink); }), 16 + 16 * g);
