@@ -394,6 +394,23 @@ int append_chunk(abnn_handle* h, const abnn_synapse* host, u64 n)
     return 0;
 }
 
+// A table that came from the host (upload, .bnn): the kernels index the per-neuron arrays with src and dst of every record,
+// so a record that names a neuron the handle does not have is refused here, and the handle is left with an empty table.
+int reset_structural(abnn_handle* h);
+int check_table(abnn_handle* h, bool allow_dead)
+{
+    u64 bad = 0;
+    CU(launch_validate_table(h->d_syn, h->n_local, (u32)h->N, (u32)h->lo, (u32)h->hi, allow_dead, h->d_total + 3, h->sm_count, h->st));
+    CU(cudaMemcpyAsync(&bad, h->d_total + 3, sizeof(u64), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (!bad) return 0;
+    h->n_local = 0; h->counts_dirty = true;
+    if (h->p.world_size == 1) h->n_local_all.assign(1, 0);
+    reset_structural(h);
+    return fail(ABNN_ERR_INVALID, std::to_string(bad) + " synapse record(s) name a neuron outside the handle's " + std::to_string(h->N) +
+                                  " neurons (src, or dst outside this rank's slice); the table was dropped");
+}
+
 // A new table (upload / init / load): the structural-step bookkeeping starts over — the whole table is the ordered region.
 int reset_structural(abnn_handle* h)
 {
@@ -862,6 +879,7 @@ int abnn_upload_synapses(abnn_handle* h, const abnn_synapse* syn, uint64_t n)
     if (!syn && n) return fail(ABNN_ERR_INVALID, "null table");
     h->n_local = 0;
     RET(append_chunk(h, syn, n));
+    RET(check_table(h, false));
     RET(sort_table(h));
     RET(reset_structural(h));
     h->counts_dirty = true;
@@ -993,6 +1011,7 @@ int abnn_load_bnn(abnn_handle* h, const char* path)
     }
     std::fclose(f);
     h->n_local = n; h->n_local_all.assign(1, n); h->counts_dirty = false;
+    RET(check_table(h, false));
     RET(sort_table(h));
     RET(reset_structural(h));
     return 0;

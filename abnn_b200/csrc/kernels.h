@@ -33,6 +33,10 @@ struct P2PTable {
 cudaError_t launch_p2p_exchange(const KParams& kp, const DevPtrs& d, const P2PTable& t, u64 n0, u64 n1, u64 head, int sm_count,
                                 cudaStream_t st);
 
+// *bad = records whose src is not a neuron of the handle (or the dead mark, if allowed) or whose dst is outside [lo, hi)
+cudaError_t launch_validate_table(const abnn_synapse* syn, u64 n, u32 n_neuron, u32 lo, u32 hi, bool allow_dead, u64* bad, int sm_count,
+                                  cudaStream_t st);
+
 // exact.cu — EXACT execution (two-phase, bit-identical to SERIAL)
 size_t exact_scan_temp_bytes(u64 span);
 // events still open against the pass-start lastFired into list[0 .. counter[0]) as (dst << 32 | event), counted per destination in

@@ -507,6 +507,30 @@ cudaError_t launch_mark_dead(const u64* list, u32 n, abnn_synapse* syn, float w_
     return cudaGetLastError();
 }
 
+// Every record of an uploaded / loaded table must name neurons of the handle: src < n_neuron (or the dead mark, where the
+// caller allows it), lo <= dst < hi. *bad counts the records that do not (the kernels index per-neuron arrays with both).
+__global__ void __launch_bounds__(256) k_validate_table(const abnn_synapse* __restrict__ syn, u64 n, u32 n_neuron, u32 lo, u32 hi,
+                                                        u32 allow_dead, u64* bad)
+{
+    u32 mine = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const uint2 sd = *reinterpret_cast<const uint2*>(syn + i);
+        const bool ok = (sd.x < n_neuron || (allow_dead && sd.x == DEAD_SRC)) && sd.y >= lo && sd.y < hi;
+        mine += !ok;
+    }
+    if (mine) atomicAdd(reinterpret_cast<unsigned long long*>(bad), (unsigned long long)mine);
+}
+cudaError_t launch_validate_table(const abnn_synapse* syn, u64 n, u32 n_neuron, u32 lo, u32 hi, bool allow_dead, u64* bad, int sm_count,
+                                  cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(u64), st);
+    if (e != cudaSuccess || !n) return e;
+    u64 blocks = (n + 255) / 256;
+    if (blocks > (u64)sm_count * 8) blocks = (u64)sm_count * 8;
+    k_validate_table<<<(unsigned)blocks, 256, 0, st>>>(syn, n, n_neuron, lo, hi, allow_dead ? 1u : 0u, bad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_grow_append(const GrowCand* c, u32 m, abnn_synapse* syn, u64 at, float w_init, cudaStream_t st)
 {
     if (!m) return cudaSuccess;

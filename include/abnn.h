@@ -263,7 +263,9 @@ int abnn_comm_init(abnn_handle* h, const void* id128);
 
 /* ---- graph: build_random_graph (brain-engine.cpp:31-53) / Brain::load|save (brain.cpp:161-178) */
 int abnn_init_graph(abnn_handle* h, uint32_t kind, uint64_t seed);
-/* Host table of the WHOLE graph (n records); the rank keeps, in order, the records whose dst it owns. */
+/* Host table of the WHOLE graph (n records); the rank keeps, in order, the records whose dst it owns.
+ * ABNN_ERR_INVALID if a kept record names a source neuron >= n_neuron, or (single rank) a destination >= n_neuron: the
+ * kernels index the per-neuron arrays with both. The handle is then left with an EMPTY table. Same for abnn_load_bnn. */
 int abnn_upload_synapses(abnn_handle* h, const abnn_synapse* syn, uint64_t n);
 /* This rank's live records, in table order. *n_out = count; fails with ABNN_ERR_CAPACITY if cap is short. */
 int abnn_download_synapses(abnn_handle* h, abnn_synapse* out, uint64_t cap, uint64_t* n_out);

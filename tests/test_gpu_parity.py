@@ -691,6 +691,22 @@ def test_error_behaviour():
         with pytest.raises(capi.AbnnError) as e:
             b.load("/nonexistent/model.bnn")
         assert e.value.status == capi.ERR_IO
+        # a record that names a neuron the handle does not have is refused (the kernels index per-neuron arrays with it),
+        # from the host table and from a .bnn file alike; the handle is left with an empty table and stays usable
+        for field in ("src", "dst"):
+            t = np.zeros(10, O.SYN_DTYPE); t["w"] = 0.5; t[field][7] = 116                 # N = 116 neurons: 0 .. 115
+            with pytest.raises(capi.AbnnError) as e:
+                b.upload_synapses(t)
+            assert e.value.status == capi.ERR_INVALID and b.info().n_syn_local == 0
+        import struct, tempfile, os
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "bad.bnn")
+            t = np.zeros(4, O.SYN_DTYPE); t["src"][2] = 0xFFFFFFFF
+            with open(path, "wb") as f:
+                f.write(struct.pack("<II", 4, 116)); f.write(t.tobytes())
+            with pytest.raises(capi.AbnnError) as e:
+                b.load(path)
+            assert e.value.status == capi.ERR_INVALID
         b.build_random_graph(1)
         assert b.run_pass(500).events == 500
     for bad in (dict(sample_block=3), dict(exec_mode=7), dict(world_size=2, rank=2), dict(exec_mode=capi.EXEC_EXACT, src_view=capi.SRC_LIVE),
