@@ -771,7 +771,9 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
     // it) and attaches an access-policy window to the handle's stream; l2_persist = 0 touches no device-wide state.
     // Tuning builds: ABNN_L2_ARRAYS = arrays covered by the window, ABNN_L2_MISS = 1 -> lines of the window that do not get
     // the persisting property are "normal" instead of "streaming".
-    if (p.l2_persist && max_persist > 0 && max_window > 0) {
+    // Only PARALLEL execution reads the arrays the window covers; a set-aside nobody fills is L2 taken away from the 64-bit
+    // arrays EXACT / SERIAL execution work on (measured: 11.0 -> 9.5 ms per EXACT pass at the 1B shape without it).
+    if (p.l2_persist && p.exec_mode == ABNN_EXEC_PARALLEL && max_persist > 0 && max_window > 0) {
         const int n_arr = tune_env("ABNN_L2_ARRAYS") ? atoi(tune_env("ABNN_L2_ARRAYS")) : 3;
         const bool miss_normal = tune_env("ABNN_L2_MISS") && atoi(tune_env("ABNN_L2_MISS")) == 1;
         // default: slack32 + the owned fire32 / vis32 (60 MB at 5M neurons on one GPU) / LIVE view: lastFired + lastVisited
