@@ -13,6 +13,8 @@ if [ "$NBOX" = "2" ]; then
 else
   runN 8 nccl --steps 100
   runN 8 peer --steps 100 --exchange peer --skip-variants
+  NCCL_ALGO=NVLS runN 8 nccl_algo_nvls --steps 100 --skip-variants          # deployment knobs of NCCL itself, not of the library
+  NCCL_PROTO=LL128 runN 8 nccl_proto_ll128 --steps 100 --skip-variants
   runN 4 nccl --steps 100
   runN 8 structural --structural --steps 128
 fi
