@@ -1,7 +1,8 @@
 """Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi`):
 two ranks, one process and one GPU each, NCCL allgather of lastFired slices inside the library,
-against the single-process OracleWorld(2) — bit-exact in SERIAL execution, including the structural
-step (local prune-compaction, allgathered growth candidates appended in event order)."""
+against the single-process OracleWorld(2) — bit-exact in SERIAL and EXACT execution, including the structural
+step (local prune-compaction, allgathered growth candidates appended in event order; eager and compact_every > 1);
+PARALLEL execution: exchanged gate words, lastVisited and statistics."""
 import socket
 
 import numpy as np
@@ -28,7 +29,7 @@ def _inputs():
     return N, syn, pre, frames
 
 
-def _gpu_worker(rank, world, port, exec_mode, q, refractory=None):
+def _gpu_worker(rank, world, port, exec_mode, q, refractory=None, extra=None, struct_all=False):
     import torch
     import torch.distributed as dist
     from abnn_b200 import distributed as D
@@ -36,7 +37,8 @@ def _gpu_worker(rank, world, port, exec_mode, q, refractory=None):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        scen = dict(SCEN, refractory=refractory) if refractory else SCEN
+        scen = dict(SCEN, refractory=refractory) if refractory else dict(SCEN)
+        scen.update(extra or {})
         base = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=exec_mode, **scen)
         b = D.create_sharded_brain(base, device=rank)
         N, syn, pre, frames = _inputs()
@@ -47,7 +49,7 @@ def _gpu_worker(rank, world, port, exec_mode, q, refractory=None):
             b.inject_inputs(vin, 1000.0); b.teacher_force(exp, float(it & 1))
             st = b.run_pass(300_000)
             stats.append((st.events, st.gated, st.fired, st.grown))
-            if it == 1:
+            if it == 1 or struct_all:
                 ss = b.prune_and_grow()
                 stats.append((ss.pruned, ss.appended, ss.n_after, ss.dropped))
         info = b.info()
@@ -149,12 +151,12 @@ def test_two_gpus_parallel_gate_word_exchange(exchange, order, engine):
     assert fired > 1000
 
 
-def _run_gpu(exec_mode, refractory=None):
+def _run_gpu(exec_mode, refractory=None, extra=None, struct_all=False):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, exec_mode, q, refractory)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, exec_mode, q, refractory, extra, struct_all)) for r in range(2)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=300) for _ in procs])
     [p.join(timeout=60) for p in procs]
@@ -162,9 +164,10 @@ def _run_gpu(exec_mode, refractory=None):
     return res
 
 
-def _run_oracle(refractory=None):
+def _run_oracle(refractory=None, extra=None, struct_all=False):
     from oracle import pyoracle as O
-    scen = dict(SCEN, refractory=refractory) if refractory else SCEN
+    scen = dict(SCEN, refractory=refractory) if refractory else dict(SCEN)
+    scen.update(extra or {})
     base = O.default_params(capi.PROFILE_NORTH_STAR, exec_mode=capi.EXEC_SERIAL, **scen)
     world = O.OracleWorld(base, 2)
     N, syn, pre, frames = _inputs()
@@ -182,13 +185,12 @@ def _run_oracle(refractory=None):
             for t in world.shards:
                 t.live_view()[1][k * half:min(N, (k + 1) * half)] = live[k * half:min(N, (k + 1) * half)]
             per_rank[k].append((sts[k].events, sts[k].gated, sts[k].fired, sts[k].grown))
-        if it == 1:
-            before = [s.n_syn_local() for s in world.shards]
+        if it == 1 or struct_all:
             pruned = [s.prune() for s in world.shards]
             allc = np.concatenate([s.grow_fetch() for s in world.shards])
             for k, s in enumerate(world.shards):
                 app, drop = s.grow_apply(allc)
-                per_rank[k].append((pruned[k], app, before[k] - pruned[k] + app, drop))
+                per_rank[k].append((pruned[k], app, s.n_syn_local(), drop))
             world._sync_counts()
     return world, per_rank, N
 
@@ -210,6 +212,47 @@ def test_two_gpus_serial_bit_exact():
         assert n_global == sum(t.n_syn_local() for t in world.shards)
         assert outs == s.read_outputs().tobytes()
     assert sum(x[1] for x in per_rank[0][:2]) > 1000
+
+
+def _assert_ranks_equal_oracle(res, world, per_rank, N):
+    half = -(-N // 2)
+    for k, s in enumerate(world.shards):
+        rank, stats, syn_b, lf_b, lv_b, clock, n_global, outs = res[k]
+        assert stats == per_rank[k], (k, stats, per_rank[k])
+        assert syn_b == s.download_synapses().tobytes()
+        assert lf_b == s.live_view()[1].tobytes()
+        assert lv_b == s.timestamps()[1][k * half:min(N, (k + 1) * half)].tobytes()
+        assert clock == s.clock
+        assert n_global == sum(t.n_syn_local() for t in world.shards)
+        assert outs == s.read_outputs().tobytes()
+
+
+def test_two_gpus_exact_bit_exact():
+    """EXACT execution on two dst-shards (per-destination buckets over the rank's own neuron slice) against the two-shard
+    oracle: pass statistics, tables, both timestamp arrays, the structural step — bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run_gpu(capi.EXEC_EXACT)
+    world, per_rank, N = _run_oracle()
+    _assert_ranks_equal_oracle(res, world, per_rank, N)
+    assert sum(x[1] for x in per_rank[0][:2]) > 1000
+
+
+@pytest.mark.parametrize("mode", [capi.EXEC_SERIAL, capi.EXEC_EXACT], ids=["serial", "exact"])
+def test_two_gpus_structural_step_every_pass_lazy_bit_exact(mode):
+    """BASELINE configs[4] regime on two dst-shards: a structural step after EVERY pass with compact_every = 2 (steps 0 and 2
+    rebuild, 1 and 3 mark dead in place and append behind the table; growth candidates allgathered, each rank appends the
+    ones it owns in tick order) — per-step counts and final tables equal the two-shard oracle bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    extra = dict(compact_every=2, w_init=0.1, table_order=capi.TABLE_DST_SORTED)
+    res = _run_gpu(mode, extra=extra, struct_all=True)
+    world, per_rank, N = _run_oracle(extra=extra, struct_all=True)
+    _assert_ranks_equal_oracle(res, world, per_rank, N)
+    steps = [x for x in per_rank[0] if len(x) == 4][1::2]               # (pruned, appended, n_after, dropped) rows
+    assert len(steps) == 4 and all(st[1] > 0 for st in steps) and any(st[0] > 0 for st in steps)
 
 
 def test_two_gpus_parallel_statistical():
