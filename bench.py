@@ -455,7 +455,9 @@ def main():
             "impl": "reference", "metric": "synaptic events/sec", "value": r["value"], "unit": "events/s", "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": "weak" if args.structural else "strong", "vs_baseline": None, "dtype": "u64 timestamps, f32 weights", "data": "synthetic",
-            "config": dict(config_dict(args, 1, "serial per dst-shard (oracle), one shard per host thread"), workload=wl,
+            "config": dict(config_dict(args, 1, "serial per dst-shard (oracle), one shard per host thread",
+                                       parallelism=f"host threads x{r['cores']} (one dst-shard each), no GPU",
+                                       l2=f"{r['syn'] * 16 / 1e9:.1f} GB table in host memory, random gathers"), workload=wl,
                            same_table_as_gpu_arm=r["same_table"], events_per_step=r["events_per_step"]),
             "cpu_baseline": {"value": r["value"], "unit": "events/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                              "one_thread": r["one_thread"], "gated_fraction": r["gated_fraction"]},
