@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -92,6 +93,7 @@ struct abnn_handle {
     u32 vec_len = 0;
     ReadoutState rs{};
     abnn_pass_stats* d_stats = nullptr;
+    bool l2_user = false;                 // holds a share of the device-wide persisting-L2 set-aside (l2_acquire / l2_release)
     void* h_pin = nullptr;                // pinned scratch (stats, scalars, spikes, rates)
     size_t h_pin_bytes = 0;
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -567,6 +569,33 @@ int run_exact(abnn_handle* h, const KParams& kp)
 
 }  // namespace
 
+// The persisting-L2 set-aside is a DEVICE-wide limit: the handles that need it share it. The first one remembers what the
+// limit was, the last one to go puts it back (a set-aside nobody fills is L2 taken away from everything else that runs on
+// the device, e.g. a later EXACT handle: 9.5 against 11.0 ms per pass).
+namespace {
+std::mutex g_l2_mu;
+int g_l2_users[64] = {};
+size_t g_l2_before[64] = {};
+}  // namespace
+void l2_acquire(abnn_handle* h, size_t before)
+{
+    if (h->device < 0 || h->device >= 64 || h->l2_user) return;
+    std::lock_guard<std::mutex> lk(g_l2_mu);
+    if (g_l2_users[h->device]++ == 0) g_l2_before[h->device] = before;
+    h->l2_user = true;
+}
+void l2_release(abnn_handle* h)
+{
+    if (!h->l2_user) return;
+    std::lock_guard<std::mutex> lk(g_l2_mu);
+    h->l2_user = false;
+    if (--g_l2_users[h->device] == 0) {
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2_before[h->device]);
+        cudaGetLastError();
+    }
+}
+
 // =================================================================================================
 extern "C" {
 
@@ -781,8 +810,11 @@ int abnn_create(const abnn_params* pp, abnn_handle** out)
                           : (size_t)(n_arr <= 1 ? 2 : 4) * npad * sizeof(u32);
         size_t want = std::min<size_t>(hot, (size_t)max_persist);
         if (tune_env("ABNN_L2_CARVE_MAX")) want = (size_t)max_persist;
-        { size_t cur = 0; if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur > want) want = cur; }
+        size_t before = 0;
+        if (cudaDeviceGetLimit(&before, cudaLimitPersistingL2CacheSize) != cudaSuccess) { before = 0; cudaGetLastError(); }
+        if (before > want) want = before;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            l2_acquire(h, before);
             size_t got = 0;
             cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
             cudaStreamAttrValue attr{};
@@ -807,6 +839,7 @@ void abnn_destroy(abnn_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
+    l2_release(h);
     for (u32 r = 0; r < P2P_MAX_WORLD; ++r) {
         if (h->p2p && r != h->p.rank && h->peer_ts[r]) cudaIpcCloseMemHandle(h->peer_ts[r]);
         if (h->p2p && r != h->p.rank && h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);

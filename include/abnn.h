@@ -173,8 +173,9 @@ typedef struct abnn_params {
     uint32_t rank;                 /* 0 .. world_size-1                                         */
     uint32_t world_size;           /* 1 = single GPU                                            */
     uint32_t l2_persist;           /* 1 (PARALLEL execution only): keep the per-neuron 32-bit arrays resident in L2: raises the
-                                      DEVICE-wide cudaLimitPersistingL2CacheSize to what they need (never lowers it) and
-                                      attaches an access-policy window to the handle's stream; 0, or SERIAL / EXACT
+                                      DEVICE-wide cudaLimitPersistingL2CacheSize to what they need and attaches an
+                                      access-policy window to the handle's stream; the limit the device had before is put
+                                      back when the last such handle of the process is destroyed. 0, or SERIAL / EXACT
                                       execution: no device-wide state is touched */
 
     /* PHILOX sampler granularity: events are drawn in groups of sample_block consecutive events that
