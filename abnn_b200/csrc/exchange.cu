@@ -1,5 +1,5 @@
 // abnn_b200/csrc/exchange.cu — the per-pass exchange of a sharded PARALLEL run as peer-memory stores over NVLink
-// instead of an NCCL collective (opt-in: ABNN_P2P_EXCHANGE=1, see capi.cu:p2p_setup).
+// instead of an NCCL collective (abnn_params.exchange = ABNN_EXCHANGE_PEER, see capi.cu:p2p_setup).
 //
 // What the exchange has to deliver before the next pass starts (capi.cu:exchange_timestamps): every rank's gate-word
 // array holds the words of EVERY neuron for the next pass, and every rank's snapshot holds rank 0's lastFired of the
