@@ -13,6 +13,9 @@ path with the same oracle. Cases (each: per-pass stats and SHA-256, first 16 hex
   toy_line_sorted the throughput configuration: ER/Beta graph, line sampler (sample_block 8), dst-sorted table,
                   pruning + growth after every pass (BASELINE configs[4] regime)
   toy_two_shards  the same as toy_line_sorted on two dst-shards (OracleWorld): summed stats, per-shard checksums
+  toy_b200_lazy   the layout bench.py runs (ABNN_PROFILE_B200: 16-record sample groups over the DST_INTERLEAVED table) with a
+                  structural step after every pass and compact_every = 3: steps 0 and 3 rebuild, the others mark dead in
+                  place and append behind the table (round 2)
 """
 import hashlib
 import json
@@ -103,7 +106,23 @@ def case_toy_two_shards():
     return out
 
 
-CASES = {"toy_reference": case_toy_reference, "toy_line_sorted": case_toy_line_sorted, "toy_two_shards": case_toy_two_shards}
+def case_toy_b200_lazy():
+    p = O.default_params(capi.PROFILE_B200, **dict(TOY, exec_mode=capi.EXEC_SERIAL, window_pre=2_000_000, refractory=100_000, seed=42,
+                                                   p_new=0.1, w_prune=0.03, w_init=0.1, syn_capacity=1_100_000, compact_every=3))
+    assert p.sample_block == 16 and p.table_order == capi.TABLE_DST_INTERLEAVED
+    o = O.OracleB(p)
+    o.init_graph(capi.GRAPH_ER_BETA, 7)
+    o.upload_timestamps(warm(10_512), None); o.clock = 2_000_000; o.set_reward(0.02)
+    out = []
+    for i in range(5):
+        st = o.run_pass(1_000_000)
+        ss = o.prune_and_grow()
+        out.append({"stats": stats(st), "structural": structural(ss), **digest(o)})
+    return out
+
+
+CASES = {"toy_reference": case_toy_reference, "toy_line_sorted": case_toy_line_sorted, "toy_two_shards": case_toy_two_shards,
+         "toy_b200_lazy": case_toy_b200_lazy}
 
 if __name__ == "__main__":
     out = {name: fn() for name, fn in CASES.items()}

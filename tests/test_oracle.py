@@ -225,9 +225,10 @@ def test_dst_sorted_table_is_a_stable_sort(oracle):
 def test_oracle_b_matches_frozen_northstar_checksums(oracle):
     """The north-star semantics have no reference implementation to pin against ("parity unpinned"):
     Oracle B is their definition. tests/golden/northstar_oracle.json freezes that definition — BASELINE configs[0]
-    (reference graph, iid sampler, sine input, 1M-event passes), the throughput configuration (line sampler, dst-sorted
-    table, pruning + growth every pass) and the same on two dst-shards — so a change of oracle_b.cpp, of its compile
-    flags or of the host toolchain that alters any result is caught here, on the CPU."""
+    (reference graph, iid sampler, sine input, 1M-event passes), the round-1 throughput configuration (line sampler,
+    dst-sorted table, pruning + growth every pass), the same on two dst-shards, and the layout bench.py runs
+    (ABNN_PROFILE_B200: 16-record groups over the interleaved table) with compact_every = 3 — so a change of oracle_b.cpp,
+    of its compile flags or of the host toolchain that alters any result is caught here, on the CPU."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_northstar_golden", os.path.join(GOLD, "make_northstar_golden.py"))
     gen = importlib.util.module_from_spec(spec)
@@ -241,6 +242,8 @@ def test_oracle_b_matches_frozen_northstar_checksums(oracle):
     last = want["toy_line_sorted"][-1]
     assert last["stats"]["gated"] > 100_000 and last["stats"]["fired"] > 1000 and last["structural"]["pruned"] > 0
     assert want["toy_reference"][-1]["structural"]["appended"] > 0
+    lazy = want["toy_b200_lazy"]
+    assert all(r["structural"]["appended"] > 0 for r in lazy) and lazy[1]["structural"]["pruned"] > 0 and lazy[3]["structural"]["pruned"] > 0
 
 
 def test_logger_matches_the_reference_logger_byte_for_byte(tmp_path):
